@@ -1,0 +1,138 @@
+/* videoprism_b200 — C ABI of the B200-native VideoPrism forward path.
+ *
+ * The reference (tmoroney/videoprism-mlx) has no FFI: its hot path sits behind a Python call
+ * surface.  Each entry point below names the reference interface it replaces; the Python shims in
+ * `videoprism-mlx_b200/models.py` present that surface on top of this ABI.
+ *
+ * Conventions: every function returns 0 on success and a negative vp_status on failure (message via
+ * vp_last_error); no exception crosses the ABI; the caller owns all I/O buffers and the stream; the
+ * handle owns the repacked weights and its workspace; all device work is enqueued on the given
+ * stream with no internal host synchronisation (the *_host variants synchronise the stream once,
+ * after the device->host copy).  A handle is bound to the CUDA device that was current at vp_create
+ * and is not thread-safe.  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VIDEOPRISM_B200_H_
+#define VIDEOPRISM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VP_API __attribute__((visibility("default")))
+#else
+#define VP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vp_handle vp_handle;
+
+typedef enum vp_status {
+  VP_OK = 0,
+  VP_ERR_INVALID = -1,     /* bad argument / shape (reference: assert / ValueError) */
+  VP_ERR_KEY = -2,         /* unknown or wrongly shaped parameter key */
+  VP_ERR_INCOMPLETE = -3,  /* vp_finalize / forward before all parameters were set */
+  VP_ERR_CUDA = -4,        /* CUDA runtime / driver failure */
+  VP_ERR_UNSUPPORTED = -5
+} vp_status;
+
+typedef enum vp_dtype { VP_F32 = 0, VP_BF16 = 1, VP_I32 = 2 } vp_dtype;
+
+typedef enum vp_model_kind {
+  VP_KIND_ENCODER = 0, /* encoders.FactorizedEncoder   (videoprism/encoders.py:391-580) */
+  VP_KIND_CLIP = 1     /* encoders.FactorizedVideoCLIP (videoprism/encoders.py:762-910) */
+} vp_model_kind;
+
+/* Mirrors the CONFIGS dict entries of videoprism/models.py:82-161 (and MODEL_CONFIGS,
+ * videoprism/models_mlx.py:14-69). */
+typedef struct vp_config {
+  int kind;                /* vp_model_kind */
+  int patch_size;          /* 18 */
+  int pos_emb_t, pos_emb_h, pos_emb_w; /* pos_emb_shape */
+  int model_dim;
+  int num_spatial_layers;
+  int num_temporal_layers;
+  int num_heads;
+  int mlp_dim;
+  float atten_logit_cap;   /* 50.0 */
+  int num_auxiliary_layers; /* CLIP only */
+  int num_unimodal_layers;  /* CLIP only */
+  int vocabulary_size;      /* CLIP only */
+} vp_config;
+
+/* -- lifecycle: replaces models.get_model (videoprism/models.py:268-303) and
+ *    models_mlx.load_video_encoder / load_model (videoprism/models_mlx.py:91-210) -------------- */
+VP_API int vp_create(const vp_config* cfg, vp_handle** out);
+VP_API void vp_destroy(vp_handle* h);
+VP_API const char* vp_last_error(const vp_handle* h); /* h may be NULL: last error of a failed vp_create */
+
+/* -- parameters: replaces models.load_pretrained_weights + utils.load_checkpoint / recover_tree
+ *    (videoprism/models.py:306-336, videoprism/utils.py:84-105,:145-169).  `flax_key` is the
+ *    '/'-joined key of the Flax checkpoint ("params/spatial_encoder/transformers_stack/x_layers/
+ *    self_attention/query/w", scan-stacked leading [L] axis); `data` is fp32, host or device memory,
+ *    C-contiguous with the given shape.  The handle repacks into its own bf16 / fp32 layouts
+ *    immediately; `data` may be freed on return. */
+VP_API int vp_set_weight(vp_handle* h, const char* flax_key, const void* data, const int64_t* shape, int ndim);
+VP_API int vp_num_weights(const vp_handle* h);                    /* number of parameter leaves expected */
+VP_API const char* vp_weight_key(const vp_handle* h, int index);  /* i-th expected flax key */
+VP_API int vp_weight_ndim(const vp_handle* h, int index);
+VP_API int64_t vp_weight_dim(const vp_handle* h, int index, int axis);
+VP_API int vp_finalize(vp_handle* h);                             /* checks completeness, precomputes constants */
+
+/* -- FactorizedEncoder.__call__ (videoprism/encoders.py:411-456, encode_with_patches :458-580).
+ *    video [B,T,H,W,3] fp32 device memory, values as the reference expects ([0,1]).
+ *    out_features [B, T*N, D] (out_dtype VP_F32 or VP_BF16).  spatial_features may be NULL, else
+ *    receives outputs['spatial_features'] [B, T*N, D] in out_dtype.  frame_paddings may be NULL, else
+ *    [B,T] fp32 device memory (1 = padded frame).  `stream` is a cudaStream_t. */
+VP_API int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                       void* out_features, void* spatial_features, int out_dtype, void* stream);
+/* Same call with HOST buffers (pageable or pinned): H2D copy of the clip batch, forward, D2H copy of
+ * the features, one stream synchronisation at the end.  Outputs are fp32. */
+VP_API int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                            float* out_features, float* spatial_features, void* stream);
+
+/* -- FactorizedVideoCLIP.__call__ (videoprism/encoders.py:784-910), video side:
+ *    vision_encoder -> auxiliary_encoder -> contrastive_vision_pooler -> (l2 normalise).
+ *    video_emb [B,D] fp32.  Optional outputs (NULL to skip), all fp32: spatial_features [B,T*N,D],
+ *    spatiotemporal_features [B,T*N,D], frame_embeddings [B,T,D]. */
+VP_API int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                          int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                          float* frame_embeddings, void* stream);
+/* -- text side: text_encoder (TextEncoder, videoprism/encoders.py:656-759) -> last token -> (l2 normalise).
+ *    ids [Q,L] int32, paddings [Q,L] fp32 (1 = pad), device memory; text_emb [Q,D] fp32. */
+VP_API int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
+                         float* text_emb, void* stream);
+VP_API int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, int normalize,
+                               float* video_emb, void* stream);
+VP_API int vp_clip_text_forward_host(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
+                              float* text_emb, void* stream);
+
+/* -- retrieval similarity (README.md:81; colab compute_similarity_matrix): sim[i,j] = v[i] . t[j].
+ *    v [Nv,D], t [Nt,D], sim [Nv,Nt], fp32 device memory. */
+VP_API int vp_similarity(const float* v, const float* t, float* sim, int Nv, int Nt, int D, void* stream);
+
+/* -- introspection ------------------------------------------------------------------------------- */
+VP_API size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W); /* device bytes a forward of this shape needs */
+VP_API int64_t vp_kernel_launches(const vp_handle* h);  /* kernels launched by this handle so far */
+VP_API int vp_device_sm_count(void);                    /* < 0 when no CUDA device is usable */
+
+/* -- kernel-level entry points (device pointers; used by the parity tests and micro-benchmarks) ---
+ *    C[M,N] = A[M,K] * Wt[N,K]^T (+bias[N]) ; act 0 none, 1 exact GELU, 2 ReLU ; optional bf16 residual. */
+VP_API int vp_gemm_bf16(const void* A, int lda, const void* Wt, int ldb, void* C, int ldc, int M, int N, int K,
+                 const float* bias, int act, const void* resid, int ldr, const float* row_scale,
+                 const float* pos_table, int pos_period, int out_f32, void* stream);
+/* y = LayerNorm(x) * gamma1 + beta over the last dim, x bf16 [M,D]; y_bf16 / y_f32 may each be NULL. */
+VP_API int vp_layernorm(const void* x, int ldx, const float* gamma1, const float* beta, void* y_bf16, float* y_f32,
+                 const float* add_table, int add_div, int add_mod, int M, int D, void* stream);
+/* patches [BT*(H/p)*(W/p), ldo] bf16 from video [BT,H,W,3] fp32 */
+VP_API int vp_patchify(const float* video, void* out, int ldo, int BT, int H, int W, int p, void* stream);
+/* attention over a packed q|k|v buffer; see csrc/kernels.h AttnArgs for the row mapping */
+VP_API int vp_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int num_seq, int S,
+                 int group, int heads, int dh, float cap, const float* key_pad, int causal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDEOPRISM_B200_H_ */

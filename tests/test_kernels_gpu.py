@@ -1,0 +1,206 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (kernel-level entry
+points) and compared with plain fp32 PyTorch / oracle functions on the same seeded inputs."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L(built_lib):
+    import videoprism_b200._lib as lib
+    return lib.lib()
+
+
+def _stream():
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def run_gemm(L, A, Wt, bias=None, act=0, resid=None, row_scale=None, pos=None, out_f32=False):
+    M, K = A.shape
+    N = Wt.shape[0]
+    Cm = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+    if resid is not None:
+        Cm.copy_(resid)
+        resid_ptr, ldr = Cm.data_ptr(), N   # in place, as the engine does
+    else:
+        resid_ptr, ldr = None, 0
+    rc = L.vp_gemm_bf16(A.data_ptr(), A.stride(0), Wt.data_ptr(), Wt.stride(0), Cm.data_ptr(), N, M, N, K, _p(bias), act,
+                        resid_ptr, ldr, _p(row_scale), _p(pos), 0 if pos is None else pos.shape[0], int(out_f32), _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    return Cm
+
+
+def ref_gemm(A, Wt, bias=None, act=0, resid=None, row_scale=None, pos=None):
+    y = A.float() @ Wt.float().T
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2)))
+    elif act == 2:
+        y = torch.relu(y)
+    if row_scale is not None:
+        y = y * row_scale[:, None]
+    if pos is not None:
+        y = y + pos[torch.arange(A.shape[0], device=A.device) % pos.shape[0]]
+    if resid is not None:
+        y = y + resid.float()
+    return y
+
+
+def _close(got, want, rtol=1.5e-2, atol=2e-2):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4g} (|want| max {want.abs().max().item():.4g})"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 768), (4096, 2304, 768), (4096, 768, 3072), (1000, 3072, 768),
+                                   (130, 192, 64), (65, 64, 128), (4096, 768, 1024), (257, 1024, 4096), (8320, 768, 768)])
+def test_gemm_plain(L, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn((M, K), device="cuda", generator=g) * 0.5).bfloat16()
+    Wt = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    _close(run_gemm(L, A, Wt, bias), ref_gemm(A, Wt, bias))
+    _close(run_gemm(L, A, Wt, bias, out_f32=True), ref_gemm(A, Wt, bias), rtol=1e-3, atol=1e-3)
+
+
+def test_gemm_is_exact_on_small_integers(L):
+    # integer-valued bf16 operands with fp32 accumulation: the result must be exact (catches any
+    # descriptor / swizzle / K-advance error that tolerance checks could hide)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randint(-3, 4, (384, 320), device="cuda", generator=g).float().bfloat16()
+    Wt = torch.randint(-3, 4, (512, 320), device="cuda", generator=g).float().bfloat16()
+    got = run_gemm(L, A, Wt, out_f32=True)
+    assert torch.equal(got, A.float() @ Wt.float().T)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_epilogues(L, act):
+    g = torch.Generator(device="cuda").manual_seed(act)
+    M, N, K = 1024 + 37, 768, 256
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    Wt = (torch.randn((N, K), device="cuda", generator=g) * 0.1).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    resid = torch.randn((M, N), device="cuda", generator=g).bfloat16()
+    rs = (torch.rand((M,), device="cuda", generator=g) > 0.3).float()
+    pos = torch.randn((256, N), device="cuda", generator=g)
+    _close(run_gemm(L, A, Wt, bias, act=act), ref_gemm(A, Wt, bias, act=act))
+    _close(run_gemm(L, A, Wt, bias, act=act, resid=resid, row_scale=rs), ref_gemm(A, Wt, bias, act=act, resid=resid, row_scale=rs))
+    _close(run_gemm(L, A, Wt, bias, act=act, pos=pos), ref_gemm(A, Wt, bias, act=act, pos=pos))
+
+
+def test_gemm_strided_operands(L):
+    # A is a column slice of a wider buffer (lda > K), as q|k|v slices are
+    g = torch.Generator(device="cuda").manual_seed(5)
+    buf = torch.randn((512, 3 * 128), device="cuda", generator=g).bfloat16()
+    A = buf[:, 128:256]
+    Wt = (torch.randn((256, 128), device="cuda", generator=g) * 0.1).bfloat16()
+    _close(run_gemm(L, A, Wt), ref_gemm(A, Wt))
+
+
+@pytest.mark.parametrize("M,D", [(1000, 768), (513, 1024), (77, 64), (4096, 768)])
+def test_layernorm(L, M, D):
+    g = torch.Generator(device="cuda").manual_seed(D)
+    x = (torch.randn((M, D), device="cuda", generator=g) * 2 + 0.5).bfloat16()
+    g1 = 1 + 0.1 * torch.randn((D,), device="cuda", generator=g)
+    b = 0.1 * torch.randn((D,), device="cuda", generator=g)
+    table = torch.randn((16, D), device="cuda", generator=g)
+    yb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+    yf = torch.empty((M, D), dtype=torch.float32, device="cuda")
+    assert L.vp_layernorm(x.data_ptr(), D, g1.data_ptr(), b.data_ptr(), yb.data_ptr(), yf.data_ptr(), table.data_ptr(), 4, 16, M, D, _stream()) == 0
+    torch.cuda.synchronize()
+    xf = x.float()
+    mu = xf.mean(-1, keepdim=True)
+    var = ((xf - mu) ** 2).mean(-1, keepdim=True)
+    ref = (xf - mu) * torch.rsqrt(var + 1e-6) * g1 + b
+    assert (yf - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    idx = (torch.arange(M, device="cuda") // 4) % 16
+    _close(yb, ref + table[idx], rtol=8e-3, atol=8e-3)
+
+
+def test_patchify_matches_reference_order(L):
+    import videoprism_oracle as O
+    BT, H, p = 3, 36, 18
+    v = torch.rand((BT, H, H, 3), device="cuda")
+    ldo = 1024
+    out = torch.zeros((BT * 4, ldo), dtype=torch.bfloat16, device="cuda")
+    assert L.vp_patchify(v.data_ptr(), out.data_ptr(), ldo, BT, H, H, p, _stream()) == 0
+    torch.cuda.synchronize()
+    ref = O.image_to_patch(v.cpu(), p).reshape(BT * 4, 972)
+    assert torch.equal(out[:, :972].cpu(), ref.bfloat16())
+    assert bool((out[:, 972:] == 0).all())
+
+
+def ref_attention(qkv, num_seq, S, group, heads, dh, cap, key_pad, causal):
+    """fp32 restatement of layers.py:601-661 on the packed layout (q pre-scaled)."""
+    D = heads * dh
+    rows = qkv.shape[0]
+    out = torch.zeros((rows, D), dtype=torch.float32, device=qkv.device)
+    sid = torch.arange(num_seq, device=qkv.device)
+    first = (sid // group) * group * S + (sid % group)
+    idx = first[:, None] + torch.arange(S, device=qkv.device)[None, :] * group     # [num_seq, S]
+    x = qkv.float()[idx]                                                            # [num_seq, S, 3D]
+    q = x[..., :D].reshape(num_seq, S, heads, dh)
+    k = x[..., D:2 * D].reshape(num_seq, S, heads, dh)
+    v = x[..., 2 * D:].reshape(num_seq, S, heads, dh)
+    logits = torch.einsum("btnh,bsnh->bnts", q, k)
+    if cap > 0:
+        logits = cap * torch.tanh(logits / cap)
+    neg = -0.7 * torch.finfo(torch.float32).max
+    masked = torch.zeros((num_seq, 1, S, S), dtype=torch.bool, device=qkv.device)
+    if key_pad is not None:
+        kp = key_pad > 0.5
+        masked = masked | kp[:, None, None, :]
+        if causal:
+            masked = masked | kp[:, None, :, None]
+    if causal:
+        i = torch.arange(S, device=qkv.device)
+        masked = masked | (i[None, :] > i[:, None])[None, None]
+    logits = torch.where(masked, torch.full_like(logits, neg), logits)
+    probs = torch.softmax(logits, dim=-1)
+    ctx = torch.einsum("bnts,bsnh->btnh", probs, v).reshape(num_seq, S, D)
+    out[idx] = ctx
+    return out
+
+
+@pytest.mark.parametrize("num_seq,S,group,heads,dh,causal,pad", [
+    (8, 256, 1, 12, 64, 0, False),      # spatial stack
+    (2 * 256, 16, 256, 12, 64, 0, False),  # temporal stack: tubes strided by N=256
+    (2 * 16, 8, 16, 2, 32, 0, True),    # temporal, T=8, dh=32, frame paddings
+    (6, 65, 1, 12, 64, 1, True),        # text tower: causal + paddings, ragged S
+    (2, 1024, 1, 4, 64, 0, False),      # auxiliary-style long sequence
+    (3, 16, 1, 2, 32, 0, True),
+    (5, 100, 1, 2, 32, 1, True),
+])
+def test_attention(L, num_seq, S, group, heads, dh, causal, pad):
+    g = torch.Generator(device="cuda").manual_seed(S + heads)
+    D = heads * dh
+    rows = num_seq * S
+    qkv = torch.randn((rows, 3 * D), device="cuda", generator=g)
+    qkv[:, :D] *= 1.5          # logits of a few units .. tens: exercises the tanh cap
+    qkv = qkv.bfloat16()
+    key_pad = None
+    if pad:
+        lens = torch.randint(1, S + 1, (num_seq,), device="cuda", generator=g)
+        lens[0] = S
+        key_pad = (torch.arange(S, device="cuda")[None, :] >= lens[:, None]).float().contiguous()
+        if not causal:
+            key_pad[-1] = 1.0   # a fully padded sequence: uniform attention, as the reference
+    out = torch.zeros((rows, D), dtype=torch.bfloat16, device="cuda")
+    rc = L.vp_attention(qkv.data_ptr(), qkv.data_ptr() + 2 * D, qkv.data_ptr() + 4 * D, 3 * D, out.data_ptr(), D, num_seq, S,
+                        group, heads, dh, 50.0, _p(key_pad), causal, _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = ref_attention(qkv, num_seq, S, group, heads, dh, 50.0, key_pad, bool(causal))
+    _close(out, ref, rtol=2e-2, atol=2e-2)

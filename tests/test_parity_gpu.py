@@ -1,0 +1,124 @@
+"""GPU parity of the whole forward (through the reference-facing surface and the C ABI) against the
+CPU oracle on the same seeded inputs and the same random-init weights.
+
+Tolerance (BASELINE.json north_star): per-token cosine similarity >= 0.999 for the bf16 path, with
+the max-abs error reported (printed) for each case."""
+import numpy as np
+import pytest
+import torch
+
+import videoprism_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.999
+
+
+def per_token_cosine(a, b):
+    a = a.reshape(-1, a.shape[-1]).astype(np.float64)
+    b = b.reshape(-1, b.shape[-1]).astype(np.float64)
+    return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1) + 1e-30)
+
+
+def report(tag, got, want):
+    cos = per_token_cosine(got, want)
+    err = np.abs(got - want).max()
+    print(f"[parity] {tag}: min cosine {cos.min():.6f}, max-abs {err:.4g}, ref max {np.abs(want).max():.4g}")
+    return cos.min(), err
+
+
+def make_model(cfg):
+    import videoprism_b200 as vp
+    kw = {k: v for k, v in cfg.items() if k != "kind"}
+    cls = vp.FactorizedEncoder if cfg["kind"] == "encoder" else vp.FactorizedVideoCLIP
+    return cls(**kw)
+
+
+def test_synthetic_state_matches_oracle_generator():
+    cfg = O.tiny_config("clip")
+    m = make_model(cfg)
+    import videoprism_b200 as vp
+    mine = vp.synthetic_state(m, seed=1234)
+    ref = O.make_synthetic_weights(cfg, seed=1234)
+    assert list(mine) == list(ref)
+    assert all(np.array_equal(mine[k], ref[k]) for k in ref)
+
+
+@pytest.mark.parametrize("T,size,pos", [(4, 16, (4, 4, 4)), (8, 32, (4, 4, 4)), (4, 16, (16, 16, 16))])
+def test_tiny_encoder_parity(T, size, pos):
+    cfg = O.tiny_config("encoder", pos_emb_shape=pos)
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(3, T, size, seed=1, kind="normal")
+    want, wouts = O.run_encoder(cfg, W, v, return_intermediate=True)
+    m = make_model(cfg)
+    got, gouts = m.apply(W, v, train=False, return_intermediate=True)
+    assert got.shape == want.shape and got.dtype == np.float32
+    c, _ = report(f"tiny encoder T={T} size={size} pos={pos}", got, want)
+    assert c >= COS_MIN
+    c2, _ = report("  spatial_features", gouts["spatial_features"], wouts["spatial_features"])
+    assert c2 >= COS_MIN
+    # device-buffer path returns the same numbers as the host-buffer path
+    got_dev, _ = m.apply(W, torch.from_numpy(v).cuda(), train=False)
+    assert np.array_equal(got_dev.cpu().numpy(), got)
+
+
+def test_tiny_encoder_frame_paddings():
+    cfg = O.tiny_config("encoder")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 4, 16, seed=2, kind="normal")
+    fp = np.zeros((2, 4), np.float32)
+    fp[0, 2:] = 1
+    want, _ = O.run_encoder(cfg, W, v, frame_paddings=torch.from_numpy(fp))
+    got, _ = make_model(cfg).apply(W, v, frame_paddings=fp)
+    c, _ = report("tiny encoder + frame_paddings", got, want)
+    assert c >= COS_MIN
+
+
+def test_tiny_clip_parity():
+    cfg = O.tiny_config("clip")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(3, 4, 16, seed=3, kind="normal")
+    ids, pad = O.make_text(5, vocab=cfg["vocabulary_size"], max_len=8)
+    pad[:, 4:] = (np.arange(4)[None, :] >= np.array([0, 1, 2, 3, 4])[:, None]).astype(np.float32)
+    ids = np.where(pad > 0, 0, ids).astype(np.int32)
+    for normalize in (True, False):
+        wv, wt, wo = O.run_clip(cfg, W, v, ids, pad, normalize=normalize, return_intermediate=True)
+        m = make_model(cfg)
+        gv, gt, go = m.apply(W, v, ids, pad, train=False, normalize=normalize, return_intermediate=True)
+        assert report(f"tiny clip video emb (normalize={normalize})", gv, wv)[0] >= COS_MIN
+        assert report(f"tiny clip text emb (normalize={normalize})", gt, wt)[0] >= COS_MIN
+        for k in ("spatial_features", "spatiotemporal_features", "frame_embeddings"):
+            assert report(f"  {k}", go[k], wo[k])[0] >= COS_MIN
+    gv2, gt2, _ = m.apply(W, v, None, None)
+    assert gt2 is None and gv2.shape == (3, cfg["model_dim"])
+    gv3, gt3, _ = m.apply(W, None, ids, pad)
+    assert gv3 is None and gt3.shape == (5, cfg["model_dim"])
+
+
+def test_base_encoder_parity_config1():
+    """BASELINE.json configs[0]: videoprism_public_v1_base, 1x16x288x288x3 (uniform [0,1) clip)."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(1, 16, 288, seed=0)
+    want, _ = O.run_encoder(cfg, W, v)
+    m = vp.get_model("videoprism_public_v1_base")
+    got, _ = m.apply(W, v, train=False)
+    assert got.shape == (1, 4096, 768)
+    c, e = report("base encoder config-1", got, want)
+    assert c >= COS_MIN
+    assert m.kernel_launches > 0
+
+
+def test_errors_mirror_reference():
+    cfg = O.tiny_config("encoder")
+    m = make_model(cfg)
+    W = O.make_synthetic_weights(cfg)
+    with pytest.raises(ValueError):       # encoders.py:86-90
+        m.apply(W, np.zeros((1, 4, 18, 18, 3), np.float32))
+    with pytest.raises(AssertionError):   # encoders.py:435
+        m.apply(W, np.zeros((1, 4, 16, 32, 3), np.float32))
+    bad = dict(W)
+    bad.pop("params/temporal_ln/bias")
+    with pytest.raises(KeyError):
+        make_model(cfg).apply(bad, np.zeros((1, 4, 16, 16, 3), np.float32))

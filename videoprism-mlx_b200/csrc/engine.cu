@@ -1,0 +1,836 @@
+// Engine: owns the repacked weights and the workspace of one model on one device and enqueues the
+// forward pass (encoder / CLIP video side / CLIP text side) as a fixed sequence of kernels on the
+// caller's stream.  Exposes the C ABI declared in include/videoprism_b200.h.
+//
+// Activation layout: tokens stay in [B, T, N, D] order (row m = (b*T + t)*N + n) through BOTH the
+// spatial and the temporal stack.  GEMMs and LayerNorms are per-token, so only the attention kernel
+// needs to know which rows form a sequence (AttnArgs::group); the reference's einshape transposes
+// (encoders.py:535, :570-572) are therefore never materialised.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/videoprism_b200.h"
+#include "kernels.h"
+
+namespace vp {
+int num_sms();
+cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D, int H, int dh, const float* wkq /*[H,D]*/,
+                        const bf16* wv /*[D, H*dh]*/, const float* bv, const bf16* wpost /*[D, H*dh]*/, const float* bpost,
+                        const float* ln_g1, const float* ln_b, int normalize, float* scratch, float* out, int64_t* launches);
+size_t pool_scratch_floats(int num_seq, int S, int D, int H, int dh);
+cudaError_t launch_pad_expand(cudaStream_t s, const float* frame_pad, float* pad_tok, float* keep_tok, float* pad_tube, int B,
+                              int T, int N);
+cudaError_t launch_similarity(cudaStream_t s, const float* v, const float* t, float* sim, int Nv, int Nt, int D);
+}  // namespace vp
+
+using vp::bf16;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t n, bool zero = false) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return e;
+    bytes = n;
+    if (zero) e = cudaMemset(p, 0, n);
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct StackWeights {
+  int L = 0, D = 0, H = 0, F = 0;
+  bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct ParamSpec {
+  std::string key;
+  std::vector<int64_t> shape;
+  std::function<cudaError_t(const float* staged, cudaStream_t s)> repack;
+  bool set = false;
+};
+
+}  // namespace
+
+struct vp_handle {
+  vp_config cfg;
+  int device = 0;
+  std::string err;
+  std::vector<ParamSpec> specs;
+  std::unordered_map<std::string, int> spec_index;
+  std::vector<void*> owned;  // device allocations holding weights
+  bool finalized = false;
+  int64_t launches = 0;
+  DevBuf staging;
+
+  // encoder
+  bf16* w_patch = nullptr; float* b_patch = nullptr; int k_patch = 0, k_patch_pad = 0;
+  std::vector<float> h_spatial_pos, h_temporal_pos;  // host copies for (re)interpolation
+  float* d_spatial_pos = nullptr; int spatial_grid_h = 0, spatial_grid_w = 0;
+  float* d_temporal_pos = nullptr; int temporal_len = 0;
+  StackWeights spatial, temporal, aux, text;
+  float *sp_ln_g = nullptr, *sp_ln_b = nullptr, *tp_ln_g = nullptr, *tp_ln_b = nullptr;
+  // pooler (collapsed single-query form, see finalize_pooler)
+  std::vector<float> h_pool_query, h_pool_wq, h_pool_bq, h_pool_wk, h_pool_pds;
+  float* pool_wkq = nullptr; bf16* pool_wv = nullptr; float* pool_bv = nullptr; bf16* pool_wpost = nullptr;
+  float *pool_bpost = nullptr, *pool_ln_g = nullptr, *pool_ln_b = nullptr;
+  // text
+  float* tok_emb = nullptr; float* cls_emb = nullptr; float* d_pe = nullptr; int pe_len = 0;
+  float *uni_ln_g = nullptr, *uni_ln_b = nullptr;
+
+  // workspace
+  DevBuf ws_x, ws_n, ws_qkv, ws_u, ws_patch, ws_misc, ws_io_in, ws_io_out, ws_pool;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+namespace {
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return h->fail(VP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(vp_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) return e;
+  h->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return cudaSuccess;
+}
+
+void add_spec(vp_handle* h, const std::string& key, std::vector<int64_t> shape,
+              std::function<cudaError_t(const float*, cudaStream_t)> fn) {
+  ParamSpec s;
+  s.key = key; s.shape = std::move(shape); s.repack = std::move(fn);
+  h->spec_index[key] = static_cast<int>(h->specs.size());
+  h->specs.push_back(std::move(s));
+}
+
+cudaError_t copy_f32(const float* src, float* dst, size_t n, cudaStream_t s) {
+  return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
+}
+
+// Parameter tree of one scan-stacked Transformer stack (layers.py:797-872).
+cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, int L, int D, int H, int F) {
+  w->L = L; w->D = D; w->H = H; w->F = F;
+  const int dh = D / H;
+  cudaError_t e;
+  if ((e = dev_alloc(h, &w->wqkv, (size_t)L * 3 * D * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->wo, (size_t)L * D * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->w1, (size_t)L * F * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->w2, (size_t)L * D * F)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->bqkv, (size_t)L * 3 * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->bo, (size_t)L * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->b1, (size_t)L * F)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->b2, (size_t)L * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->ln1_g, (size_t)L * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->ln1_b, (size_t)L * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->ln2_g, (size_t)L * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->ln2_b, (size_t)L * D)) != cudaSuccess) return e;
+  const std::string p = prefix + "/x_layers";
+  // query scale dh^-0.5 (layers.py:569-584, internal_enable_per_dim_scale=False) is folded into Wq, bq.
+  const float qscale = 1.0f / sqrtf(static_cast<float>(dh));
+  StackWeights ww = *w;
+  add_spec(h, p + "/layer_norm/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+    return vp::launch_affine_f32(st, s, ww.ln1_g, (size_t)L * D, 1.0f, 1.0f); });
+  add_spec(h, p + "/layer_norm/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+    return copy_f32(s, ww.ln1_b, (size_t)L * D, st); });
+  const char* names[3] = {"query", "key", "value"};
+  for (int i = 0; i < 3; ++i) {
+    const float sc = (i == 0) ? qscale : 1.0f;
+    add_spec(h, p + "/self_attention/" + names[i] + "/w", {L, D, H, dh}, [ww, L, D, i, sc](const float* s, cudaStream_t st) {
+      for (int l = 0; l < L; ++l) {   // [D, (H dh)] -> rows [i*D, (i+1)*D) of the fused [3D, D] K-major weight
+        cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * D * D, ww.wqkv + (size_t)l * 3 * D * D + (size_t)i * D * D,
+                                                  D, D, D, sc);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaSuccess; });
+    add_spec(h, p + "/self_attention/" + names[i] + "/b", {L, H, dh}, [ww, L, D, i, sc](const float* s, cudaStream_t st) {
+      for (int l = 0; l < L; ++l) {
+        cudaError_t e = vp::launch_affine_f32(st, s + (size_t)l * D, ww.bqkv + (size_t)l * 3 * D + (size_t)i * D, D, sc, 0.f);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaSuccess; });
+  }
+  // post.w is [D_out, (H dh)]: already the K-major [N, K] layout the GEMM wants (layers.py:483).
+  add_spec(h, p + "/self_attention/post/w", {L, D, H, dh}, [ww, L, D](const float* s, cudaStream_t st) {
+    return vp::launch_cast_bf16(st, s, ww.wo, (size_t)L * D * D, 1.0f); });
+  add_spec(h, p + "/self_attention/post/b", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+    return copy_f32(s, ww.bo, (size_t)L * D, st); });
+  add_spec(h, p + "/ff_layer/layer_norm/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+    return vp::launch_affine_f32(st, s, ww.ln2_g, (size_t)L * D, 1.0f, 1.0f); });
+  add_spec(h, p + "/ff_layer/layer_norm/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+    return copy_f32(s, ww.ln2_b, (size_t)L * D, st); });
+  add_spec(h, p + "/ff_layer/ffn_layer1/linear/kernel", {L, D, F}, [ww, L, D, F](const float* s, cudaStream_t st) {
+    for (int l = 0; l < L; ++l) {
+      cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * D * F, ww.w1 + (size_t)l * F * D, D, F, D, 1.0f);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess; });
+  add_spec(h, p + "/ff_layer/ffn_layer1/linear/bias", {L, F}, [ww, L, F](const float* s, cudaStream_t st) {
+    return copy_f32(s, ww.b1, (size_t)L * F, st); });
+  add_spec(h, p + "/ff_layer/ffn_layer2/linear/kernel", {L, F, D}, [ww, L, D, F](const float* s, cudaStream_t st) {
+    for (int l = 0; l < L; ++l) {
+      cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * F * D, ww.w2 + (size_t)l * D * F, F, D, F, 1.0f);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess; });
+  add_spec(h, p + "/ff_layer/ffn_layer2/linear/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+    return copy_f32(s, ww.b2, (size_t)L * D, st); });
+  return cudaSuccess;
+}
+
+cudaError_t add_ln(vp_handle* h, const std::string& prefix, float** g, float** b, int D) {
+  cudaError_t e;
+  if ((e = dev_alloc(h, g, D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, b, D)) != cudaSuccess) return e;
+  float* gg = *g; float* bb = *b;
+  add_spec(h, prefix + "/scale", {D}, [gg, D](const float* s, cudaStream_t st) { return vp::launch_affine_f32(st, s, gg, D, 1.0f, 1.0f); });
+  add_spec(h, prefix + "/bias", {D}, [bb, D](const float* s, cudaStream_t st) { return copy_f32(s, bb, D, st); });
+  return cudaSuccess;
+}
+
+cudaError_t host_copy(std::vector<float>* dst, const float* staged, size_t n, cudaStream_t st) {
+  dst->resize(n);
+  cudaError_t e = cudaMemcpyAsync(dst->data(), staged, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
+
+cudaError_t add_encoder(vp_handle* h, const std::string& prefix) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, P = c.patch_size;
+  h->k_patch = P * P * 3;
+  h->k_patch_pad = (h->k_patch + 63) / 64 * 64;
+  cudaError_t e;
+  if ((e = dev_alloc(h, &h->w_patch, (size_t)D * h->k_patch_pad)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->b_patch, D)) != cudaSuccess) return e;
+  vp_handle* hh = h;
+  add_spec(h, prefix + "/patch_projection/linear/kernel", {h->k_patch, D}, [hh, D](const float* s, cudaStream_t st) {
+    return vp::launch_transpose_cast(st, s, hh->w_patch, hh->k_patch, D, hh->k_patch_pad, 1.0f); });
+  add_spec(h, prefix + "/patch_projection/linear/bias", {D}, [hh, D](const float* s, cudaStream_t st) {
+    return copy_f32(s, hh->b_patch, D, st); });
+  add_spec(h, prefix + "/spatial_pos_emb/emb_var", {(int64_t)c.pos_emb_h * c.pos_emb_w, D}, [hh, D](const float* s, cudaStream_t st) {
+    hh->spatial_grid_h = hh->spatial_grid_w = 0;
+    return host_copy(&hh->h_spatial_pos, s, (size_t)hh->cfg.pos_emb_h * hh->cfg.pos_emb_w * D, st); });
+  add_spec(h, prefix + "/temporal_pos_emb/emb_var", {c.pos_emb_t, D}, [hh, D](const float* s, cudaStream_t st) {
+    hh->temporal_len = 0;
+    return host_copy(&hh->h_temporal_pos, s, (size_t)hh->cfg.pos_emb_t * D, st); });
+  if ((e = add_stack(h, prefix + "/spatial_encoder/transformers_stack", &h->spatial, c.num_spatial_layers, D, c.num_heads, c.mlp_dim)) != cudaSuccess) return e;
+  if ((e = add_stack(h, prefix + "/temporal_encoder/transformers_stack", &h->temporal, c.num_temporal_layers, D, c.num_heads, c.mlp_dim)) != cudaSuccess) return e;
+  if ((e = add_ln(h, prefix + "/spatial_ln", &h->sp_ln_g, &h->sp_ln_b, D)) != cudaSuccess) return e;
+  if ((e = add_ln(h, prefix + "/temporal_ln", &h->tp_ln_g, &h->tp_ln_b, D)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t add_clip_extras(vp_handle* h) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, H = c.num_heads;
+  const int ph = 4 * D / H;  // pooler dim_per_head: hidden 4*D over H heads (encoders.py:861, layers.py:708-713)
+  cudaError_t e;
+  if (c.num_auxiliary_layers > 0) {
+    if ((e = add_stack(h, "params/auxiliary_encoder/transformers_stack", &h->aux, c.num_auxiliary_layers, D, H, c.mlp_dim)) != cudaSuccess) return e;
+  }
+  vp_handle* hh = h;
+  const std::string pp = "params/contrastive_vision_pooler";
+  if ((e = dev_alloc(h, &h->pool_wkq, (size_t)H * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->pool_wv, (size_t)H * ph * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->pool_bv, (size_t)H * ph)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->pool_wpost, (size_t)D * H * ph)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->pool_bpost, D)) != cudaSuccess) return e;
+  add_spec(h, pp + "/pooling_attention_query", {1, D}, [hh, D](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_query, s, D, st); });
+  add_spec(h, pp + "/pooling_attention/query/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_wq, s, (size_t)D * H * ph, st); });
+  add_spec(h, pp + "/pooling_attention/query/b", {H, ph}, [hh, H, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_bq, s, (size_t)H * ph, st); });
+  add_spec(h, pp + "/pooling_attention/key/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_wk, s, (size_t)D * H * ph, st); });
+  // key bias shifts every score of a head by the same constant -> cancels in the softmax; accepted, unused.
+  add_spec(h, pp + "/pooling_attention/key/b", {H, ph}, [](const float*, cudaStream_t) { return cudaSuccess; });
+  add_spec(h, pp + "/pooling_attention/value/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) {
+    return vp::launch_cast_bf16(st, s, hh->pool_wv, (size_t)D * H * ph, 1.0f); });  // kept [D, (H dh)]: pool_ctx_kernel reads it j-contiguous
+  add_spec(h, pp + "/pooling_attention/value/b", {H, ph}, [hh, H, ph](const float* s, cudaStream_t st) { return copy_f32(s, hh->pool_bv, (size_t)H * ph, st); });
+  add_spec(h, pp + "/pooling_attention/post/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) {
+    return vp::launch_cast_bf16(st, s, hh->pool_wpost, (size_t)D * H * ph, 1.0f); });
+  add_spec(h, pp + "/pooling_attention/post/b", {D}, [hh, D](const float* s, cudaStream_t st) { return copy_f32(s, hh->pool_bpost, D, st); });
+  add_spec(h, pp + "/pooling_attention/per_dim_scale/per_dim_scale", {ph}, [hh, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_pds, s, ph, st); });
+  if ((e = add_ln(h, pp + "/pooling_attention_layer_norm", &h->pool_ln_g, &h->pool_ln_b, D)) != cudaSuccess) return e;
+  // text tower (encoders.py:656-759): mlp_dim = 4 * model_dim (:897)
+  const std::string tp = "params/text_encoder";
+  if ((e = dev_alloc(h, &h->tok_emb, (size_t)c.vocabulary_size * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->cls_emb, D)) != cudaSuccess) return e;
+  add_spec(h, tp + "/token_emb/emb_var", {c.vocabulary_size, D}, [hh, D](const float* s, cudaStream_t st) {
+    return copy_f32(s, hh->tok_emb, (size_t)hh->cfg.vocabulary_size * D, st); });
+  add_spec(h, tp + "/cls_emb", {1, 1, D}, [hh, D](const float* s, cudaStream_t st) { return copy_f32(s, hh->cls_emb, D, st); });
+  if ((e = add_stack(h, tp + "/unimodal_transformer", &h->text, c.num_unimodal_layers, D, H, 4 * D)) != cudaSuccess) return e;
+  if ((e = add_ln(h, tp + "/unimodal_ln", &h->uni_ln_g, &h->uni_ln_b, D)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+// jax.image.resize(..., 'bilinear') weights (antialias=True default): triangle kernel, half-pixel
+// centres, widened by 1/scale when down-sampling, renormalised per output (encoders.py:124-126,:157-161).
+std::vector<float> resize_weights(int n_in, int n_out) {
+  std::vector<float> w((size_t)n_in * n_out, 0.f);
+  const double inv_scale = (double)n_in / n_out;
+  const double kscale = inv_scale > 1.0 ? inv_scale : 1.0;
+  for (int o = 0; o < n_out; ++o) {
+    const double sf = (o + 0.5) * inv_scale - 0.5;
+    double tot = 0.0;
+    for (int i = 0; i < n_in; ++i) {
+      double x = fabs(sf - i) / kscale;
+      double v = x < 1.0 ? 1.0 - x : 0.0;
+      w[(size_t)i * n_out + o] = (float)v;
+      tot += v;
+    }
+    const bool inside = sf >= -0.5 && sf <= n_in - 0.5;
+    for (int i = 0; i < n_in; ++i) {
+      float& v = w[(size_t)i * n_out + o];
+      v = (inside && fabs(tot) > 1000.0 * 1.1920929e-7) ? (float)(v / tot) : 0.f;
+    }
+  }
+  return w;
+}
+
+int prepare_pos_tables(vp_handle* h, int T, int gh, int gw, cudaStream_t st) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim;
+  if (h->spatial_grid_h != gh || h->spatial_grid_w != gw) {
+    std::vector<float> tab;
+    if (gh == c.pos_emb_h && gw == c.pos_emb_w) {
+      tab = h->h_spatial_pos;
+    } else {  // _interpolate_emb_2d, encoders.py:131-165 (separable)
+      std::vector<float> wh = resize_weights(c.pos_emb_h, gh), ww = resize_weights(c.pos_emb_w, gw);
+      std::vector<float> tmp((size_t)gh * c.pos_emb_w * D, 0.f);
+      for (int o = 0; o < gh; ++o)
+        for (int i = 0; i < c.pos_emb_h; ++i) {
+          const float w = wh[(size_t)i * gh + o];
+          if (w == 0.f) continue;
+          for (int x = 0; x < c.pos_emb_w * D; ++x) tmp[(size_t)o * c.pos_emb_w * D + x] += w * h->h_spatial_pos[(size_t)i * c.pos_emb_w * D + x];
+        }
+      tab.assign((size_t)gh * gw * D, 0.f);
+      for (int y = 0; y < gh; ++y)
+        for (int o = 0; o < gw; ++o)
+          for (int i = 0; i < c.pos_emb_w; ++i) {
+            const float w = ww[(size_t)i * gw + o];
+            if (w == 0.f) continue;
+            for (int d = 0; d < D; ++d) tab[((size_t)y * gw + o) * D + d] += w * tmp[((size_t)y * c.pos_emb_w + i) * D + d];
+          }
+    }
+    if (h->d_spatial_pos) { cudaFree(h->d_spatial_pos); h->d_spatial_pos = nullptr; }
+    CK(cudaMalloc(&h->d_spatial_pos, tab.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(h->d_spatial_pos, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->spatial_grid_h = gh; h->spatial_grid_w = gw;
+  }
+  if (h->temporal_len != T) {
+    std::vector<float> tab;
+    if (T == c.pos_emb_t) {
+      tab = h->h_temporal_pos;
+    } else {  // _interpolate_emb_1d, encoders.py:107-128
+      std::vector<float> wt = resize_weights(c.pos_emb_t, T);
+      tab.assign((size_t)T * D, 0.f);
+      for (int o = 0; o < T; ++o)
+        for (int i = 0; i < c.pos_emb_t; ++i) {
+          const float w = wt[(size_t)i * T + o];
+          if (w == 0.f) continue;
+          for (int d = 0; d < D; ++d) tab[(size_t)o * D + d] += w * h->h_temporal_pos[(size_t)i * D + d];
+        }
+    }
+    if (h->d_temporal_pos) { cudaFree(h->d_temporal_pos); h->d_temporal_pos = nullptr; }
+    CK(cudaMalloc(&h->d_temporal_pos, tab.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(h->d_temporal_pos, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->temporal_len = T;
+  }
+  return VP_OK;
+}
+
+// Pooler constants.  The pooling query is a learned parameter, so the projected, PerDimScale'd query
+// qh[h,:] = (query . Wq[:,h,:] + bq[h,:]) * 1.442695041/sqrt(dh) * softplus(pds)   (layers.py:502-527,:1093)
+// is a constant, and scores[s,h] = x[s] . (Wk[:,h,:] qh[h,:]) + const(h): fold to wkq [H, D].
+int finalize_pooler(vp_handle* h) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, H = c.num_heads, ph = 4 * D / H;
+  std::vector<double> qh((size_t)H * ph);
+  for (int hh = 0; hh < H; ++hh)
+    for (int j = 0; j < ph; ++j) {
+      double acc = h->h_pool_bq[(size_t)hh * ph + j];
+      for (int d = 0; d < D; ++d) acc += (double)h->h_pool_query[d] * h->h_pool_wq[((size_t)d * H + hh) * ph + j];
+      const double p = h->h_pool_pds[j];
+      const double softplus = p > 30.0 ? p : log1p(exp(p));
+      qh[(size_t)hh * ph + j] = acc * (1.442695041 / sqrt((double)ph)) * softplus;
+    }
+  std::vector<float> wkq((size_t)H * D);
+  for (int hh = 0; hh < H; ++hh)
+    for (int d = 0; d < D; ++d) {
+      double acc = 0.0;
+      for (int j = 0; j < ph; ++j) acc += (double)h->h_pool_wk[((size_t)d * H + hh) * ph + j] * qh[(size_t)hh * ph + j];
+      wkq[(size_t)hh * D + d] = (float)acc;
+    }
+  CK(cudaMemcpy(h->pool_wkq, wkq.data(), wkq.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->h_pool_wq.clear(); h->h_pool_wq.shrink_to_fit();
+  h->h_pool_wk.clear(); h->h_pool_wk.shrink_to_fit();
+  return VP_OK;
+}
+
+// PositionalEmbedding (encoders.py:240-266), float32 arithmetic as the reference.
+int prepare_pe(vp_handle* h, int L, cudaStream_t st) {
+  if (h->pe_len == L) return VP_OK;
+  const int D = h->cfg.model_dim, nts = D / 2;
+  std::vector<float> pe((size_t)L * D, 0.f);
+  const float inc = (float)(log(10000.0) / fmax((double)((float)nts - 1.0f), 1.0));
+  for (int p = 0; p < L; ++p)
+    for (int i = 0; i < nts; ++i) {
+      const float inv = expf((float)i * -inc);
+      const float stime = (float)p * inv;
+      pe[(size_t)p * D + i] = sinf(stime);
+      pe[(size_t)p * D + nts + i] = cosf(stime);
+    }
+  if (h->d_pe) { cudaFree(h->d_pe); h->d_pe = nullptr; }
+  CK(cudaMalloc(&h->d_pe, pe.size() * sizeof(float)));
+  CK(cudaMemcpyAsync(h->d_pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  h->pe_len = L;
+  return VP_OK;
+}
+
+struct SeqLayout {
+  int num_seq, S, group, causal;
+  const float* key_pad;    // [num_seq, S] or null
+  const float* row_scale;  // [M] or null
+};
+
+// One Transformer stack (layers.py:989-1041) over the bf16 residual stream x [M, D] (in place).
+int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayout& sl, int act, cudaStream_t st) {
+  const int D = w.D, F = w.F, H = w.H;
+  bf16* n = static_cast<bf16*>(h->ws_n.p);
+  bf16* qkv = static_cast<bf16*>(h->ws_qkv.p);
+  bf16* u = static_cast<bf16*>(h->ws_u.p);
+  for (int l = 0; l < w.L; ++l) {
+    vp::LnArgs ln;
+    ln.x = x; ln.ldx = D; ln.gamma1 = w.ln1_g + (size_t)l * D; ln.beta = w.ln1_b + (size_t)l * D; ln.y_bf16 = n; ln.M = M; ln.D = D;
+    CK(vp::launch_layernorm(st, ln)); h->launches++;
+    vp::GemmEpilogue e1;
+    e1.bias = w.bqkv + (size_t)l * 3 * D;
+    CK(vp::launch_gemm(st, n, D, w.wqkv + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->launches++;
+    vp::AttnArgs at;
+    at.q = qkv; at.k = qkv + D; at.v = qkv + 2 * D; at.ld = 3 * D; at.out = n; at.ldo = D;
+    at.num_seq = sl.num_seq; at.S = sl.S; at.group = sl.group; at.heads = H; at.dh = D / H;
+    at.cap = h->cfg.atten_logit_cap; at.key_pad = sl.key_pad; at.causal = sl.causal;
+    CK(vp::launch_attention(st, at)); h->launches++;
+    vp::GemmEpilogue e2;
+    e2.bias = w.bo + (size_t)l * D; e2.resid = x; e2.ldr = D;
+    CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, x, D, M, D, D, e2)); h->launches++;
+    ln.gamma1 = w.ln2_g + (size_t)l * D; ln.beta = w.ln2_b + (size_t)l * D;
+    CK(vp::launch_layernorm(st, ln)); h->launches++;
+    vp::GemmEpilogue e3;
+    e3.bias = w.b1 + (size_t)l * F; e3.act = act; e3.row_scale = sl.row_scale;
+    CK(vp::launch_gemm(st, n, D, w.w1 + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->launches++;
+    vp::GemmEpilogue e4;
+    e4.bias = w.b2 + (size_t)l * D; e4.row_scale = sl.row_scale; e4.resid = x; e4.ldr = D;
+    CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, x, D, M, D, F, e4)); h->launches++;
+  }
+  return VP_OK;
+}
+
+int ensure_workspace(vp_handle* h, size_t M, int D, int F) {
+  CK(h->ws_x.ensure(M * D * sizeof(bf16)));
+  CK(h->ws_n.ensure(M * D * sizeof(bf16)));
+  CK(h->ws_qkv.ensure(M * 3 * D * sizeof(bf16)));
+  CK(h->ws_u.ensure(M * F * sizeof(bf16)));
+  return VP_OK;
+}
+
+int check_ready(vp_handle* h) {
+  if (h == nullptr) return VP_ERR_INVALID;
+  if (!h->finalized) return h->fail(VP_ERR_INCOMPLETE, "vp_finalize has not been called");
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device) {
+    if (cudaSetDevice(h->device) != cudaSuccess) return h->fail(VP_ERR_CUDA, "cannot select device %d", h->device);
+  }
+  return VP_OK;
+}
+
+// Shared body of the encoder forward.  Leaves the final (pre-temporal_ln) residual stream in ws_x and
+// writes LN outputs where requested.  Returns the token count through *M_out.
+int encoder_body(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
+                 bf16* out_bf16, float* spatial_f32, cudaStream_t st, size_t* M_out) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, P = c.patch_size;
+  if (B <= 0 || T <= 0) return h->fail(VP_ERR_INVALID, "empty batch (B=%d, T=%d)", B, T);
+  if (H != W) return h->fail(VP_ERR_INVALID, "H (%d) must equal W (%d) (encoders.py:435)", H, W);
+  if (H % P || W % P) return h->fail(VP_ERR_INVALID, "Image height (%d) and width (%d) should be multiples of patch_size (%d)", H, W, P);
+  const int gh = H / P, gw = W / P, N = gh * gw;
+  const size_t M = (size_t)B * T * N;
+  if (M > 0x7fffffffULL / (size_t)(3 * D > c.mlp_dim ? 3 * D : c.mlp_dim)) return h->fail(VP_ERR_INVALID, "batch too large");
+  int rc;
+  if ((rc = prepare_pos_tables(h, T, gh, gw, st)) != VP_OK) return rc;
+  if ((rc = ensure_workspace(h, M, D, c.mlp_dim)) != VP_OK) return rc;
+  CK(h->ws_patch.ensure(M * h->k_patch_pad * sizeof(bf16), /*zero=*/true));
+  bf16* x = static_cast<bf16*>(h->ws_x.p);
+  bf16* patches = static_cast<bf16*>(h->ws_patch.p);
+
+  const float *pad_tok = nullptr, *keep_tok = nullptr, *pad_tube = nullptr;
+  if (frame_pad != nullptr) {
+    CK(h->ws_misc.ensure(3 * M * sizeof(float)));
+    float* base = static_cast<float*>(h->ws_misc.p);
+    CK(vp::launch_pad_expand(st, frame_pad, base, base + M, base + 2 * M, B, T, N)); h->launches++;
+    pad_tok = base; keep_tok = base + M; pad_tube = base + 2 * M;
+  }
+
+  // patchify + cast (encoders.py:436-439), patch projection + spatial pos-emb (:488-514)
+  CK(vp::launch_patchify(st, video, patches, h->k_patch_pad, B * T, H, W, P)); h->launches++;
+  vp::GemmEpilogue ep;
+  ep.bias = h->b_patch; ep.pos_table = h->d_spatial_pos; ep.pos_period = N;
+  CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->launches++;
+
+  // spatial stack: sequences = frames (N contiguous tokens)
+  SeqLayout sp{B * T, N, 1, 0, pad_tok, keep_tok};
+  if ((rc = run_stack(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st)) != VP_OK) return rc;
+
+  // spatial_ln (+ temporal pos-emb add, encoders.py:528-553); in place on the residual stream
+  vp::LnArgs ln;
+  ln.x = x; ln.ldx = D; ln.gamma1 = h->sp_ln_g; ln.beta = h->sp_ln_b; ln.y_bf16 = x; ln.y_f32 = spatial_f32;
+  ln.add_table = h->d_temporal_pos; ln.add_div = N; ln.add_mod = T; ln.M = (int)M; ln.D = D;
+  CK(vp::launch_layernorm(st, ln)); h->launches++;
+
+  // temporal stack: sequences = tubes (T tokens, N rows apart)
+  SeqLayout tp{B * N, T, N, 0, pad_tube, keep_tok};
+  if ((rc = run_stack(h, h->temporal, x, (int)M, tp, vp::ACT_GELU, st)) != VP_OK) return rc;
+
+  // temporal_ln (:567-569); '(bn)td->b(tn)d' (:570-572) is the identity in this layout
+  vp::LnArgs lo;
+  lo.x = x; lo.ldx = D; lo.gamma1 = h->tp_ln_g; lo.beta = h->tp_ln_b; lo.y_bf16 = out_bf16; lo.y_f32 = out_f32; lo.M = (int)M; lo.D = D;
+  CK(vp::launch_layernorm(st, lo)); h->launches++;
+  if (M_out) *M_out = M;
+  return VP_OK;
+}
+
+}  // namespace
+
+// ===================================================================== C ABI
+extern "C" {
+
+int vp_create(const vp_config* cfg, vp_handle** out) {
+  if (out == nullptr || cfg == nullptr) { g_create_error = "null argument"; return VP_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->model_dim <= 0 || cfg->num_heads <= 0 || cfg->model_dim % cfg->num_heads || cfg->patch_size <= 0 ||
+      (cfg->patch_size % 2) || cfg->mlp_dim <= 0 || (cfg->model_dim % 8) || (cfg->mlp_dim % 8)) {
+    g_create_error = "invalid config (model_dim/num_heads/patch_size/mlp_dim)";
+    return VP_ERR_INVALID;
+  }
+  const int dh = cfg->model_dim / cfg->num_heads;
+  if (dh != 64 && dh != 32) { g_create_error = "dim_per_head must be 32 or 64"; return VP_ERR_UNSUPPORTED; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+    return VP_ERR_CUDA;
+  }
+  vp_handle* h = new vp_handle();
+  h->cfg = *cfg;
+  cudaGetDevice(&h->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, h->device);
+  if (prop.major != 10) {
+    g_create_error = "device is not sm_100 (B200): compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    delete h;
+    return VP_ERR_UNSUPPORTED;
+  }
+  e = add_encoder(h, cfg->kind == VP_KIND_CLIP ? "params/vision_encoder" : "params");
+  if (e == cudaSuccess && cfg->kind == VP_KIND_CLIP) e = add_clip_extras(h);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("allocation failed: ") + cudaGetErrorString(e);
+    vp_destroy(h);
+    return VP_ERR_CUDA;
+  }
+  *out = h;
+  return VP_OK;
+}
+
+void vp_destroy(vp_handle* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->d_spatial_pos) cudaFree(h->d_spatial_pos);
+  if (h->d_temporal_pos) cudaFree(h->d_temporal_pos);
+  if (h->d_pe) cudaFree(h->d_pe);
+  DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool};
+  for (DevBuf* b : bufs) b->release();
+  delete h;
+}
+
+const char* vp_last_error(const vp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vp_num_weights(const vp_handle* h) { return h ? (int)h->specs.size() : 0; }
+const char* vp_weight_key(const vp_handle* h, int i) { return (h && i >= 0 && i < (int)h->specs.size()) ? h->specs[i].key.c_str() : nullptr; }
+int vp_weight_ndim(const vp_handle* h, int i) { return (h && i >= 0 && i < (int)h->specs.size()) ? (int)h->specs[i].shape.size() : -1; }
+int64_t vp_weight_dim(const vp_handle* h, int i, int axis) {
+  if (!h || i < 0 || i >= (int)h->specs.size() || axis < 0 || axis >= (int)h->specs[i].shape.size()) return -1;
+  return h->specs[i].shape[axis];
+}
+
+int vp_set_weight(vp_handle* h, const char* key, const void* data, const int64_t* shape, int ndim) {
+  if (h == nullptr || key == nullptr || data == nullptr || (ndim > 0 && shape == nullptr)) return VP_ERR_INVALID;
+  cudaSetDevice(h->device);
+  auto it = h->spec_index.find(key);
+  if (it == h->spec_index.end()) return h->fail(VP_ERR_KEY, "unknown parameter key '%s'", key);
+  ParamSpec& sp = h->specs[it->second];
+  bool same = (int)sp.shape.size() == ndim;
+  size_t count = 1;
+  for (int i = 0; same && i < ndim; ++i) same = sp.shape[i] == shape[i];
+  if (!same) return h->fail(VP_ERR_KEY, "parameter '%s' has the wrong shape", key);
+  for (int64_t d : sp.shape) count *= (size_t)d;
+  CK(h->staging.ensure(count * sizeof(float)));
+  CK(cudaMemcpy(h->staging.p, data, count * sizeof(float), cudaMemcpyDefault));
+  CK(sp.repack(static_cast<const float*>(h->staging.p), 0));
+  CK(cudaStreamSynchronize(0));
+  sp.set = true;
+  h->finalized = false;
+  return VP_OK;
+}
+
+int vp_finalize(vp_handle* h) {
+  if (h == nullptr) return VP_ERR_INVALID;
+  cudaSetDevice(h->device);
+  for (const ParamSpec& s : h->specs)
+    if (!s.set) return h->fail(VP_ERR_INCOMPLETE, "parameter '%s' was never set", s.key.c_str());
+  if (h->cfg.kind == VP_KIND_CLIP) {
+    int rc = finalize_pooler(h);
+    if (rc != VP_OK) return rc;
+  }
+  h->staging.release();
+  h->finalized = true;
+  return VP_OK;
+}
+
+int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                       void* out_features, void* spatial_features, int out_dtype, void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
+  if (out_dtype != VP_F32 && out_dtype != VP_BF16) return h->fail(VP_ERR_INVALID, "out_dtype must be VP_F32 or VP_BF16");
+  if (spatial_features != nullptr && out_dtype != VP_F32) return h->fail(VP_ERR_UNSUPPORTED, "spatial_features requires VP_F32 outputs");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return encoder_body(h, video, B, T, H, W, frame_paddings, out_dtype == VP_F32 ? static_cast<float*>(out_features) : nullptr,
+                      out_dtype == VP_BF16 ? static_cast<bf16*>(out_features) : nullptr, static_cast<float*>(spatial_features), st, nullptr);
+}
+
+int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                            float* out_features, float* spatial_features, void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || H % h->cfg.patch_size || W % h->cfg.patch_size) return h->fail(VP_ERR_INVALID, "bad clip shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_elems = (size_t)B * T * H * W * 3;
+  const size_t N = (size_t)(H / h->cfg.patch_size) * (W / h->cfg.patch_size);
+  const size_t out_elems = (size_t)B * T * N * h->cfg.model_dim;
+  const size_t pad_bytes = frame_paddings ? (size_t)B * T * sizeof(float) : 0;
+  CK(h->ws_io_in.ensure(in_elems * sizeof(float) + 256 + pad_bytes));
+  CK(h->ws_io_out.ensure(out_elems * sizeof(float) * (spatial_features ? 2 : 1)));
+  float* d_in = static_cast<float*>(h->ws_io_in.p);
+  float* d_pad = nullptr;
+  CK(cudaMemcpyAsync(d_in, video, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (frame_paddings) {
+    d_pad = reinterpret_cast<float*>(reinterpret_cast<char*>(d_in) + ((in_elems * sizeof(float) + 255) / 256) * 256);
+    CK(cudaMemcpyAsync(d_pad, frame_paddings, pad_bytes, cudaMemcpyHostToDevice, st));
+  }
+  float* d_out = static_cast<float*>(h->ws_io_out.p);
+  float* d_sp = spatial_features ? d_out + out_elems : nullptr;
+  rc = encoder_body(h, d_in, B, T, H, W, d_pad, d_out, nullptr, d_sp, st, nullptr);
+  if (rc != VP_OK) return rc;
+  CK(cudaMemcpyAsync(out_features, d_out, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (spatial_features) CK(cudaMemcpyAsync(spatial_features, d_sp, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return VP_OK;
+}
+
+int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                          int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                          float* frame_embeddings, void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
+  if (video == nullptr || video_emb == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim;
+  size_t M = 0;
+  // vision_encoder (encoders.py:822-841).  Its output (after temporal_ln) becomes the residual
+  // stream of the auxiliary encoder, so LN writes bf16 back into ws_x.
+  rc = encoder_body(h, video, B, T, H, W, frame_paddings, spatiotemporal_features, static_cast<bf16*>(h->ws_x.p), spatial_features, st, &M);
+  if (rc != VP_OK) return rc;
+  bf16* x = static_cast<bf16*>(h->ws_x.p);
+  const int N = (int)(M / ((size_t)B * T));
+  if (c.num_auxiliary_layers > 0) {  // auxiliary_encoder: full attention over all T*N tokens of a clip (:846-857)
+    SeqLayout ax{B, T * N, 1, 0, nullptr, nullptr};
+    if ((rc = run_stack(h, h->aux, x, (int)M, ax, vp::ACT_GELU, st)) != VP_OK) return rc;
+  }
+  const int ph = 4 * D / c.num_heads;
+  size_t need = vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph);
+  size_t need_f = frame_embeddings ? vp::pool_scratch_floats(B * T, N, D, c.num_heads, ph) : 0;
+  CK(h->ws_pool.ensure((need > need_f ? need : need_f) * sizeof(float)));
+  CK(vp::launch_pool(st, x, B, T * N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
+                     h->pool_ln_g, h->pool_ln_b, normalize, static_cast<float*>(h->ws_pool.p), video_emb, &h->launches));
+  if (frame_embeddings) {  // same pooler on the per-frame token sets (:874-885)
+    CK(vp::launch_pool(st, x, B * T, N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
+                       h->pool_ln_g, h->pool_ln_b, normalize, static_cast<float*>(h->ws_pool.p), frame_embeddings, &h->launches));
+  }
+  return VP_OK;
+}
+
+int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize, float* text_emb,
+                         void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
+  if (ids == nullptr || text_emb == nullptr) return h->fail(VP_ERR_INVALID, "null ids / output pointer");
+  if (paddings == nullptr) return h->fail(VP_ERR_INVALID, "Text paddings are required. (encoders.py:888)");
+  if (Q <= 0 || L <= 0) return h->fail(VP_ERR_INVALID, "empty text batch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, S = L + 1;
+  const size_t M = (size_t)Q * S;
+  if ((rc = prepare_pe(h, L, st)) != VP_OK) return rc;
+  if ((rc = ensure_workspace(h, M, D, 4 * D)) != VP_OK) return rc;
+  CK(h->ws_misc.ensure(3 * M * sizeof(float)));
+  float* keep = static_cast<float*>(h->ws_misc.p);
+  float* pad_ext = keep + M;
+  bf16* x = static_cast<bf16*>(h->ws_x.p);
+  CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->launches++;
+  SeqLayout tl{Q, S, 1, 1, pad_ext, keep};
+  if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st)) != VP_OK) return rc;
+  // unimodal_ln on the class token only (features[:, -1], encoders.py:756-758,:906), then l2 normalise
+  float* tmp = static_cast<float*>(h->ws_misc.p) + 2 * M;
+  vp::LnArgs ln;
+  ln.x = x + (size_t)L * D; ln.ldx = S * D; ln.gamma1 = h->uni_ln_g; ln.beta = h->uni_ln_b;
+  ln.y_f32 = normalize ? tmp : text_emb; ln.M = Q; ln.D = D;
+  CK(vp::launch_layernorm(st, ln)); h->launches++;
+  if (normalize) { CK(vp::launch_l2norm(st, tmp, text_emb, Q, D)); h->launches++; }
+  return VP_OK;
+}
+
+int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, int normalize, float* video_emb,
+                               void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (video == nullptr || video_emb == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return h->fail(VP_ERR_INVALID, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_elems = (size_t)B * T * H * W * 3;
+  CK(h->ws_io_in.ensure(in_elems * sizeof(float)));
+  CK(h->ws_io_out.ensure((size_t)B * h->cfg.model_dim * sizeof(float)));
+  CK(cudaMemcpyAsync(h->ws_io_in.p, video, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = vp_clip_video_forward(h, static_cast<const float*>(h->ws_io_in.p), B, T, H, W, nullptr, normalize,
+                             static_cast<float*>(h->ws_io_out.p), nullptr, nullptr, nullptr, stream);
+  if (rc != VP_OK) return rc;
+  CK(cudaMemcpyAsync(video_emb, h->ws_io_out.p, (size_t)B * h->cfg.model_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return VP_OK;
+}
+
+int vp_clip_text_forward_host(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
+                              float* text_emb, void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (ids == nullptr || paddings == nullptr || text_emb == nullptr || Q <= 0 || L <= 0) return h->fail(VP_ERR_INVALID, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)Q * L;
+  CK(h->ws_io_in.ensure(n * 8 + 256));
+  CK(h->ws_io_out.ensure((size_t)Q * h->cfg.model_dim * sizeof(float)));
+  int32_t* d_ids = static_cast<int32_t*>(h->ws_io_in.p);
+  float* d_pad = reinterpret_cast<float*>(d_ids + n);
+  CK(cudaMemcpyAsync(d_ids, ids, n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_pad, paddings, n * 4, cudaMemcpyHostToDevice, st));
+  rc = vp_clip_text_forward(h, d_ids, d_pad, Q, L, normalize, static_cast<float*>(h->ws_io_out.p), stream);
+  if (rc != VP_OK) return rc;
+  CK(cudaMemcpyAsync(text_emb, h->ws_io_out.p, (size_t)Q * h->cfg.model_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return VP_OK;
+}
+
+int vp_similarity(const float* v, const float* t, float* sim, int Nv, int Nt, int D, void* stream) {
+  if (!v || !t || !sim || Nv <= 0 || Nt <= 0 || D <= 0) return VP_ERR_INVALID;
+  return vp::launch_similarity(static_cast<cudaStream_t>(stream), v, t, sim, Nv, Nt, D) == cudaSuccess ? VP_OK : VP_ERR_CUDA;
+}
+
+size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W) {
+  if (!h || B <= 0 || T <= 0 || H <= 0 || W <= 0) return 0;
+  const vp_config& c = h->cfg;
+  const size_t N = (size_t)(H / c.patch_size) * (W / c.patch_size);
+  const size_t M = (size_t)B * T * N;
+  const size_t D = c.model_dim, F = c.mlp_dim;
+  return M * (5 * D + F + h->k_patch_pad) * sizeof(bf16);
+}
+
+int64_t vp_kernel_launches(const vp_handle* h) { return h ? h->launches : 0; }
+
+int vp_device_sm_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return -1;
+  return vp::num_sms();
+}
+
+// ------------------------------------------------------------ kernel-level entry points
+static int ck(cudaError_t e) { return e == cudaSuccess ? VP_OK : (e == cudaErrorInvalidValue ? VP_ERR_INVALID : VP_ERR_CUDA); }
+
+int vp_gemm_bf16(const void* A, int lda, const void* Wt, int ldb, void* C, int ldc, int M, int N, int K, const float* bias,
+                 int act, const void* resid, int ldr, const float* row_scale, const float* pos_table, int pos_period,
+                 int out_f32, void* stream) {
+  vp::GemmEpilogue e;
+  e.bias = bias; e.act = act; e.resid = static_cast<const bf16*>(resid); e.ldr = ldr; e.row_scale = row_scale;
+  e.pos_table = pos_table; e.pos_period = pos_period; e.out_f32 = out_f32;
+  return ck(vp::launch_gemm(static_cast<cudaStream_t>(stream), static_cast<const bf16*>(A), lda, static_cast<const bf16*>(Wt), ldb, C,
+                            ldc, M, N, K, e));
+}
+
+int vp_layernorm(const void* x, int ldx, const float* gamma1, const float* beta, void* y_bf16, float* y_f32,
+                 const float* add_table, int add_div, int add_mod, int M, int D, void* stream) {
+  vp::LnArgs a;
+  a.x = static_cast<const bf16*>(x); a.ldx = ldx; a.gamma1 = gamma1; a.beta = beta; a.y_bf16 = static_cast<bf16*>(y_bf16);
+  a.y_f32 = y_f32; a.add_table = add_table; a.add_div = add_div > 0 ? add_div : 1; a.add_mod = add_mod > 0 ? add_mod : 1;
+  a.M = M; a.D = D;
+  return ck(vp::launch_layernorm(static_cast<cudaStream_t>(stream), a));
+}
+
+int vp_patchify(const float* video, void* out, int ldo, int BT, int H, int W, int p, void* stream) {
+  return ck(vp::launch_patchify(static_cast<cudaStream_t>(stream), video, static_cast<bf16*>(out), ldo, BT, H, W, p));
+}
+
+int vp_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int num_seq, int S, int group,
+                 int heads, int dh, float cap, const float* key_pad, int causal, void* stream) {
+  vp::AttnArgs a;
+  a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.ld = ld;
+  a.out = static_cast<bf16*>(out); a.ldo = ldo; a.num_seq = num_seq; a.S = S; a.group = group; a.heads = heads; a.dh = dh;
+  a.cap = cap; a.key_pad = key_pad; a.causal = causal;
+  return ck(vp::launch_attention(static_cast<cudaStream_t>(stream), a));
+}
+
+}  // extern "C"
