@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Headline benchmark: clips/s of the VideoPrism FactorizedEncoder forward (16x288x288x3 clips).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model base|large] [--global-batch 32]
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): videoprism_public_v1_base, batch 32 synthetic clips, bf16 tensor-core
+math with fp32 accumulation, the batch sharded contiguously over the N GPUs of one node (32/N clips per
+rank, no inter-GPU traffic inside the encoder).  One "step" = one forward of the whole batch.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM), `e2e` is the
+same metric through the public API with host buffers (H2D of the clips and D2H of the features inside the
+timed region), `roofline` is the dominant kernel (FFN1 GEMM) against the measured bf16 peak, and
+`cpu_baseline` is the oracle on the host cores (N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_PER_CLIP = {"base": 973.29, "large": 2998.52}          # BASELINE.md §3 (2*M*N*K per GEMM + 4*S^2*dh*H per sequence)
+MODEL_NAME = {"base": "videoprism_public_v1_base", "large": "videoprism_public_v1_large"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 300.0] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+def cpu_oracle_clips_per_s(model: str, steps: int, warmup: int, budget_s: float):
+    """The reference's CPU path: fp32 PyTorch-CPU restatement of the Flax forward (oracle/), 1 clip per step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import videoprism_oracle as O
+    cfg = O.CONFIGS[MODEL_NAME[model]]
+    W = O.to_torch(O.make_synthetic_weights(cfg))
+    v = torch.from_numpy(O.make_video(1, 16, 288, seed=0))
+    times = []
+    t_begin = time.perf_counter()
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.encoder_forward(cfg, W, v)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if time.perf_counter() - t_begin > budget_s and times:
+                break
+    mean = sum(times) / len(times)
+    return 1.0 / mean, len(times), torch.get_num_threads(), mean
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, n_steps, threads, mean = cpu_oracle_clips_per_s(args.model, args.steps, min(args.warmup, 1), budget_s=200.0)
+    sample = f"1 clip (1x16x288x288x3) per step, {n_steps} timed steps, mean {mean:.2f} s/clip"
+    line = {
+        "impl": "reference", "metric": "clips/sec (16x288^2 encoder forward)", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": n_steps, "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODEL_NAME[args.model]} encoder forward, 16x288x288x3 clips", "global_batch": 1},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "PyTorch-CPU fp32 restatement of the reference Flax path (jax/flax not installable offline)"},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="base", choices=["base", "large"])
+    ap.add_argument("--global-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+
+    import videoprism_b200 as vp
+    name = MODEL_NAME[args.model]
+    model = vp.get_model(name)
+    state = vp.synthetic_state(model, seed=1234)
+    model.load_state(state)
+
+    if args.global_batch % world:
+        raise SystemExit("--global-batch must be divisible by the number of GPUs")
+    b_local = args.global_batch // world
+    T, S = 16, 288
+    # rotate device input buffers so the clips read by consecutive steps never sit in the 126 MB L2
+    clip_bytes = T * S * S * 3 * 4
+    n_bufs = max(2, -(-512 * 2**20 // (b_local * clip_bytes)))
+    rng = np.random.default_rng(rank)
+    host_in = torch.from_numpy(rng.random((b_local, T, S, S, 3), dtype=np.float32)).pin_memory()
+    bufs = [host_in.cuda(non_blocking=True) for _ in range(n_bufs)]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        return model(bufs[i % n_bufs])[0]
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    launches0 = model.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        step(i)
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = model.kernel_launches - launches0
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = args.global_batch * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: host buffers through the public API (pinned H2D of the clips + D2H of the features every step)
+    e2e = None
+    if not args.no_e2e:
+        host_np = host_in.numpy()
+        out_bytes = b_local * T * 256 * model.config["model_dim"] * 4
+        for i in range(2):
+            model(host_np)
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            model(host_np)       # returns numpy features: the call synchronises after the D2H copy
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.global_batch * n_e2e / float(tt.item()), "unit": "clips/s", "h2d_bytes_per_step": b_local * clip_bytes,
+               "d2h_bytes_per_step": out_bytes, "steps": n_e2e,
+               "how": "models.FactorizedEncoder.__call__(numpy) -> vp_encoder_forward_host: H2D + forward + D2H per step, wall clock, max over ranks"}
+
+    # ---- roofline of the dominant kernel (FFN1 GEMM + GELU epilogue), CUDA events on the launch stream
+    peaks, peak_src = measured_peaks()
+    roof = None
+    if rank == 0:
+        import videoprism_b200._lib as L
+        lib = L.lib()
+        D, F = model.config["model_dim"], model.config["mlp_dim"]
+        M = b_local * T * 256
+        A = (torch.randn((M, D), device="cuda") * 0.5).bfloat16()
+        Wt = (torch.randn((F, D), device="cuda") * 0.02).bfloat16()
+        bias = torch.zeros((F,), device="cuda")
+        Cm = torch.empty((M, F), dtype=torch.bfloat16, device="cuda")
+        st = int(torch.cuda.current_stream().cuda_stream)
+        def gemm():
+            rc = lib.vp_gemm_bf16(A.data_ptr(), D, Wt.data_ptr(), D, Cm.data_ptr(), F, M, F, D, bias.data_ptr(), 1, None, 0, None, None, 0, 0, st)
+            assert rc == 0
+        for _ in range(3):
+            gemm()
+        torch.cuda.synchronize()
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gemm()
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        flops = 2.0 * M * F * D
+        ach = flops / (k_ms * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        fwd_tf = value / world * GF_PER_CLIP[args.model] / 1e3
+        roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel<256,GELU> FFN1 [{M}x{D}]x[{D}x{F}]", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src + ", bf16_tflops_sustained",
+                "ms_per_launch": k_ms, "flops_per_launch": flops,
+                "forward": {"achieved": fwd_tf, "frac": fwd_tf / peak, "gflop_per_clip": GF_PER_CLIP[args.model],
+                            "note": "whole forward per GPU = clips/s/GPU x algorithmic GF/clip"}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, n_steps, threads, mean = cpu_oracle_clips_per_s(args.model, 1, 0, budget_s=60.0)
+        cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+               "sample": f"1 clip (1x16x288x288x3), {n_steps} run, {mean:.2f} s; fp32 PyTorch-CPU restatement of the Flax path (oracle/)"}
+
+    if rank == 0:
+        line = {
+            "metric": "clips/sec (16x288^2 encoder forward)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{name} encoder forward, 16x288x288x3 clips, random-init weights", "global_batch": args.global_batch,
+                       "clips_per_gpu": b_local, "parallelism": f"dp{world} (batch shard, no collective)",
+                       "l2": f"inputs larger than L2: {n_bufs} rotating device input buffers of {b_local * clip_bytes / 2**20:.0f} MiB"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -481,7 +481,7 @@ int check_ready(vp_handle* h) {
 // Shared body of the encoder forward.  Leaves the final (pre-temporal_ln) residual stream in ws_x and
 // writes LN outputs where requested.  Returns the token count through *M_out.
 int encoder_body(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
-                 bf16* out_bf16, float* spatial_f32, cudaStream_t st, size_t* M_out) {
+                 bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
   const vp_config& c = h->cfg;
   const int D = c.model_dim, P = c.patch_size;
   if (B <= 0 || T <= 0) return h->fail(VP_ERR_INVALID, "empty batch (B=%d, T=%d)", B, T);
@@ -527,7 +527,8 @@ int encoder_body(vp_handle* h, const float* video, int B, int T, int H, int W, c
 
   // temporal_ln (:567-569); '(bn)td->b(tn)d' (:570-572) is the identity in this layout
   vp::LnArgs lo;
-  lo.x = x; lo.ldx = D; lo.gamma1 = h->tp_ln_g; lo.beta = h->tp_ln_b; lo.y_bf16 = out_bf16; lo.y_f32 = out_f32; lo.M = (int)M; lo.D = D;
+  lo.x = x; lo.ldx = D; lo.gamma1 = h->tp_ln_g; lo.beta = h->tp_ln_b; lo.y_bf16 = final_ln_in_place ? x : out_bf16; lo.y_f32 = out_f32;
+  lo.M = (int)M; lo.D = D;
   CK(vp::launch_layernorm(st, lo)); h->launches++;
   if (M_out) *M_out = M;
   return VP_OK;
@@ -640,7 +641,7 @@ int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, in
   if (spatial_features != nullptr && out_dtype != VP_F32) return h->fail(VP_ERR_UNSUPPORTED, "spatial_features requires VP_F32 outputs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return encoder_body(h, video, B, T, H, W, frame_paddings, out_dtype == VP_F32 ? static_cast<float*>(out_features) : nullptr,
-                      out_dtype == VP_BF16 ? static_cast<bf16*>(out_features) : nullptr, static_cast<float*>(spatial_features), st, nullptr);
+                      out_dtype == VP_BF16 ? static_cast<bf16*>(out_features) : nullptr, false, static_cast<float*>(spatial_features), st, nullptr);
 }
 
 int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
@@ -665,7 +666,7 @@ int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int 
   }
   float* d_out = static_cast<float*>(h->ws_io_out.p);
   float* d_sp = spatial_features ? d_out + out_elems : nullptr;
-  rc = encoder_body(h, d_in, B, T, H, W, d_pad, d_out, nullptr, d_sp, st, nullptr);
+  rc = encoder_body(h, d_in, B, T, H, W, d_pad, d_out, nullptr, false, d_sp, st, nullptr);
   if (rc != VP_OK) return rc;
   CK(cudaMemcpyAsync(out_features, d_out, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (spatial_features) CK(cudaMemcpyAsync(spatial_features, d_sp, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -686,7 +687,7 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   size_t M = 0;
   // vision_encoder (encoders.py:822-841).  Its output (after temporal_ln) becomes the residual
   // stream of the auxiliary encoder, so LN writes bf16 back into ws_x.
-  rc = encoder_body(h, video, B, T, H, W, frame_paddings, spatiotemporal_features, static_cast<bf16*>(h->ws_x.p), spatial_features, st, &M);
+  rc = encoder_body(h, video, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
   if (rc != VP_OK) return rc;
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   const int N = (int)(M / ((size_t)B * T));
@@ -721,15 +722,16 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
   const size_t M = (size_t)Q * S;
   if ((rc = prepare_pe(h, L, st)) != VP_OK) return rc;
   if ((rc = ensure_workspace(h, M, D, 4 * D)) != VP_OK) return rc;
-  CK(h->ws_misc.ensure(3 * M * sizeof(float)));
+  const size_t Mp = (M + 63) & ~static_cast<size_t>(63);  // keeps the sub-buffers 16-byte aligned (float4 stores)
+  CK(h->ws_misc.ensure((2 * Mp + (size_t)Q * D) * sizeof(float)));
   float* keep = static_cast<float*>(h->ws_misc.p);
-  float* pad_ext = keep + M;
+  float* pad_ext = keep + Mp;
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->launches++;
   SeqLayout tl{Q, S, 1, 1, pad_ext, keep};
   if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st)) != VP_OK) return rc;
   // unimodal_ln on the class token only (features[:, -1], encoders.py:756-758,:906), then l2 normalise
-  float* tmp = static_cast<float*>(h->ws_misc.p) + 2 * M;
+  float* tmp = static_cast<float*>(h->ws_misc.p) + 2 * Mp;
   vp::LnArgs ln;
   ln.x = x + (size_t)L * D; ln.ldx = S * D; ln.gamma1 = h->uni_ln_g; ln.beta = h->uni_ln_b;
   ln.y_f32 = normalize ? tmp : text_emb; ln.M = Q; ln.D = D;
