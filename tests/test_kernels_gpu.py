@@ -100,6 +100,25 @@ def test_gemm_epilogues(L, act):
     _close(run_gemm(L, A, Wt, bias, act=act, pos=pos), ref_gemm(A, Wt, bias, act=act, pos=pos))
 
 
+def test_gelu_epilogue_accuracy(L):
+    """The epilogue's GELU (tanh form with a fitted inner polynomial + MUFU.TANH) against exact erf GELU
+    (layers.py:31) over every bf16 input in [-12, 12]: feed x through a rank-1 product so acc == x exactly."""
+    xs = torch.unique(torch.linspace(-12, 12, 200001, device="cuda").bfloat16())
+    N = (xs.numel() + 7) // 8 * 8
+    x = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    x[: xs.numel()] = xs
+    A = torch.zeros((128, 64), device="cuda", dtype=torch.bfloat16); A[:, 0] = 1
+    Wt = torch.zeros((N, 64), device="cuda", dtype=torch.bfloat16); Wt[:, 0] = x
+    got = run_gemm(L, A, Wt, act=1, out_f32=True)[0].double()
+    xd = x.double()
+    want = 0.5 * xd * (1 + torch.erf(xd / math.sqrt(2)))
+    err = (got - want).abs()
+    print(f"[gelu] max abs err {err.max().item():.3g} at x={xd[err.argmax()].item():.4g}; "
+          f"max err / max(|y|, 2^-8) {(err / want.abs().clamp_min(2**-8)).max().item():.3g}")
+    assert err.max().item() < 5e-4                                    # far inside bf16 output rounding for |y| >~ 0.1
+    assert (err / want.abs().clamp_min(2 ** -8)).max().item() < 8e-3  # ~2 bf16 ulps relative, abs 3e-5 near zero
+
+
 def test_gemm_strided_operands(L):
     # A is a column slice of a wider buffer (lda > K), as q|k|v slices are
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -4,10 +4,17 @@
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles)
 //   warp 1      : MMA issuer    (one elected thread, tcgen05.mma kind::f16, M=128 x N=BN x K=16)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue      (tcgen05.ld -> bias / GELU / row-scale / pos-emb / residual -> global)
-// The fp32 accumulator lives in TMEM and is double buffered (2 x BN columns), so the epilogue
-// of tile i overlaps the main loop of tile i+1.  The smem ring has kStages slots of
-// (128 x 64 A, BN x 64 B) bf16.
+//   warps 4..11 : epilogue      (tcgen05.ld -> bias / GELU / row-scale / pos-emb / residual -> bf16)
+// The fp32 accumulator lives in TMEM and is double buffered (2 x BN columns), so the epilogue of
+// tile i overlaps the main loop of tile i+1.  The smem ring has kStages slots of (128 x 64 A,
+// BN x 64 B) bf16.
+//
+// Epilogue data movement is all TMA: each epilogue warp owns 32 accumulator rows and walks its
+// columns in 32-column chunks; a chunk is converted in registers (packed f32x2 math), written to a
+// per-warp 32x32 bf16 staging tile (64B swizzle, conflict-free, two ping-pong buffers) and stored
+// with cp.async.bulk.tensor; the bf16 residual tile is TMA-loaded into the same staging buffer
+// ahead of time and added in place.  (Row-per-thread global stores cost 32 L1 wavefronts per
+// instruction and made the K=768 GEMMs epilogue-bound.)
 //
 // Replaces the reference's nn.Dense / einsum projections (layers.py:304-312, :486-488, :483-498).
 #include <cuda.h>
@@ -25,6 +32,8 @@ constexpr int BK = 64;
 constexpr int kNumThreads = 384;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kStageTileBytes = 32 * 32 * 2;            // one 32x32 bf16 staging tile
+constexpr int kStagingBytes = kNumEpiWarps * 2 * kStageTileBytes;  // 32 KB
 
 template <int BN>
 struct Cfg {
@@ -33,7 +42,8 @@ struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 struct KParams {
@@ -48,21 +58,24 @@ struct KParams {
   int ldr;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int ACT, bool OUT_F32>
+template <int BN, int ACT, bool RESID, bool OUT_F32>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const KParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
-  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr (4 B)
+  const uint32_t staging_base = smem_base + C::kPipeBytes;
+  const uint32_t bar_base = staging_base + kStagingBytes;
+  // barriers (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], resid[8 warps][2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4);
+  auto resid_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * 2 + b); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4 + 2 * kNumEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,6 +88,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (!OUT_F32) tma_prefetch_desc(&tmC);
+    if (RESID) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -84,6 +99,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kNumEpiWarps);
+    }
+    for (int w = 0; w < kNumEpiWarps; ++w) {
+      mbar_init(resid_bar(w, 0), 1);
+      mbar_init(resid_bar(w, 1), 1);
     }
     fence_mbar_init();
   }
@@ -153,85 +172,158 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int half = e >> 2;         // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
+    constexpr int NCH = kColsPerWarp / 32;
+    const uint32_t stg = staging_base + e * 2 * kStageTileBytes;
+    uint32_t rphase0 = 0, rphase1 = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / num_n_tiles) * BM;
       const int n0 = (tile % num_n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
+      const int mrow0 = m0 + q * 32;
+      const int ncol0 = n0 + half * kColsPerWarp;
+      if (RESID && !OUT_F32) {
+        // prefetch the residual tiles of the first two chunks into the two staging buffers
+        if (lane == 0) {
+          tma_store_wait_read<1>();   // the store that last used buffer 0 has drained
+          mbar_expect_tx(resid_bar(e, 0), kStageTileBytes);
+          tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
+          if (NCH > 1) {
+            tma_store_wait_read<0>();
+            mbar_expect_tx(resid_bar(e, 1), kStageTileBytes);
+            tma_load_2d(stg + kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
+      const int m = mrow0 + lane;
       const bool row_ok = m < p.M;
       const float rscale = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + m) : 1.0f;
+      const f32x2 rscale2 = pk2(rscale, rscale);
       const float* pos_row = nullptr;
       if (p.pos_table != nullptr) pos_row = p.pos_table + static_cast<size_t>(m % p.pos_period) * p.N;
-      const bf16* res_row = (p.resid != nullptr) ? p.resid + static_cast<size_t>(m) * p.ldr : nullptr;
 #pragma unroll 1
-      for (int ch = 0; ch < kColsPerWarp / 32; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
         const int col = half * kColsPerWarp + ch * 32;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + col + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
-        if (ch == kColsPerWarp / 32 - 1) {
+        if (ch == NCH - 1) {
           // all TMEM reads of this warp for this tile are done: release the accumulator early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         const int n = n0 + col;
-        if (row_ok && n < p.N) {
+        f32x2 v[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int ng = n + g * 8;
-            if (ng < p.N) {
-              float v[8];
+        for (int i = 0; i < 16; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
+        if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ng + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (ACT == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-              } else if (ACT == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-              }
-              if (p.row_scale != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= rscale;
-              }
-              if (pos_row != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + ng));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + ng + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (res_row != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_row + ng);
-                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-              }
-              if (OUT_F32) {
-                float* cp = reinterpret_cast<float*>(p.C) + static_cast<size_t>(m) * p.ldc + ng;
-                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                bf16* cp = reinterpret_cast<bf16*>(p.C) + static_cast<size_t>(m) * p.ldc + ng;
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(cp) = o;
-              }
+          for (int g = 0; g < 8; ++g) {
+            if (n + g * 4 < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + g * 4));
+              v[2 * g] = add2(v[2 * g], pk2(b.x, b.y));
+              v[2 * g + 1] = add2(v[2 * g + 1], pk2(b.z, b.w));
             }
           }
         }
+        if (ACT == ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu2(v[i]);
+        } else if (ACT == ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a, b;
+            upk2(v[i], a, b);
+            v[i] = pk2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+          }
+        }
+        if (p.row_scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = mul2(v[i], rscale2);
+        }
+        if (pos_row != nullptr && row_ok) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (n + g * 4 < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + n + g * 4));
+              v[2 * g] = add2(v[2 * g], pk2(b.x, b.y));
+              v[2 * g + 1] = add2(v[2 * g + 1], pk2(b.z, b.w));
+            }
+          }
+        }
+        if (OUT_F32) {
+          // diagnostic / test path: direct fp32 stores (residual, if any, read directly)
+          if (row_ok) {
+            float* cp = reinterpret_cast<float*>(p.C) + static_cast<size_t>(m) * p.ldc + n;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (n + g * 4 < p.N) {
+                float a, b, c, d;
+                upk2(v[2 * g], a, b);
+                upk2(v[2 * g + 1], c, d);
+                if (RESID) {
+                  const uint2 rr = *reinterpret_cast<const uint2*>(p.resid + static_cast<size_t>(m) * p.ldr + n + g * 4);
+                  a += bf16_lo(rr.x); b += bf16_hi(rr.x); c += bf16_lo(rr.y); d += bf16_hi(rr.y);
+                }
+                *reinterpret_cast<float4*>(cp + g * 4) = make_float4(a, b, c, d);
+              }
+            }
+          }
+        } else {
+          const int b = ch & 1;
+          const uint32_t buf = stg + b * kStageTileBytes;
+          // 64-byte rows, 16-byte chunk c of row `lane` lives at chunk (c ^ ((lane >> 1) & 3))  (TMA SWIZZLE_64B)
+          const uint32_t rowaddr = buf + lane * 64;
+          const int sw = (lane >> 1) & 3;
+          if (RESID) {
+            mbar_wait(resid_bar(e, b), b ? rphase1 : rphase0);
+            if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(rowaddr + ((c ^ sw) << 4)));
+              v[4 * c + 0] = add2(v[4 * c + 0], pk2(bf16_lo(w0), bf16_hi(w0)));
+              v[4 * c + 1] = add2(v[4 * c + 1], pk2(bf16_lo(w1), bf16_hi(w1)));
+              v[4 * c + 2] = add2(v[4 * c + 2], pk2(bf16_lo(w2), bf16_hi(w2)));
+              v[4 * c + 3] = add2(v[4 * c + 3], pk2(bf16_lo(w3), bf16_hi(w3)));
+            }
+          } else {
+            if (lane == 0) tma_store_wait_read<1>();   // the store issued two chunks ago (same buffer) has drained
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float lo, hi;
+              upk2(v[4 * c + j], lo, hi);
+              w[j] = pack_bf16x2(lo, hi);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((c ^ sw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n, mrow0);   // clipped against [M, N] by the tensor map
+            tma_store_commit();
+            if (RESID && ch + 2 < NCH) {
+              // buffer (ch+1)&1 ... is busy; the buffer for chunk ch+2 is this one: wait for the store just issued
+              // to finish reading it, then prefetch that chunk's residual tile
+              tma_store_wait_read<0>();
+              mbar_expect_tx(resid_bar(e, b), kStageTileBytes);
+              tma_load_2d(buf, &tmR, resid_bar(e, b), n + 64, mrow0);
+            }
+          }
+          __syncwarp();
+        }
       }
     }
+    if (!OUT_F32 && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -263,18 +355,19 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 // 2-D bf16 tensor map: inner dim `cols` (contiguous), outer dim `rows` with row pitch `ld` elements,
-// box = box_cols x box_rows, 128B swizzle, zero fill out of bounds.
+// box = box_cols x box_rows, zero fill out of bounds.  swizzle_bytes: 128 or 64 (= box_cols * 2).
 bool make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                       uint32_t box_rows, uint32_t box_cols) {
+                       uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * sizeof(bf16)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -289,33 +382,42 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int ACT, bool OUT_F32>
-static cudaError_t launch_gemm_t(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, int grid) {
-  auto kern = gemm_bf16_kernel<BN, ACT, OUT_F32>;
+namespace {
+
+struct Maps {
+  CUtensorMap a, b, c, r;
+};
+
+template <int BN, int ACT, bool RESID, bool OUT_F32>
+cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp, int grid) {
+  auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  kern<<<grid, kNumThreads, Cfg<BN>::kSmemBytes, s>>>(ta, tb, kp);
+  kern<<<grid, kNumThreads, Cfg<BN>::kSmemBytes, s>>>(m.a, m.b, m.c, m.r, kp);
   return cudaGetLastError();
 }
 
-template <int BN>
-static cudaError_t launch_gemm_bn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, int grid,
-                                  int act, int out_f32) {
-  if (out_f32) {
-    if (act == ACT_NONE) return launch_gemm_t<BN, ACT_NONE, true>(s, ta, tb, kp, grid);
-    return cudaErrorInvalidValue;
-  }
+template <int BN, bool RESID, bool OUT_F32>
+cudaError_t launch_gemm_act(cudaStream_t s, const Maps& m, const KParams& kp, int grid, int act) {
   switch (act) {
-    case ACT_NONE: return launch_gemm_t<BN, ACT_NONE, false>(s, ta, tb, kp, grid);
-    case ACT_GELU: return launch_gemm_t<BN, ACT_GELU, false>(s, ta, tb, kp, grid);
-    case ACT_RELU: return launch_gemm_t<BN, ACT_RELU, false>(s, ta, tb, kp, grid);
+    case ACT_NONE: return launch_gemm_t<BN, ACT_NONE, RESID, OUT_F32>(s, m, kp, grid);
+    case ACT_GELU: return launch_gemm_t<BN, ACT_GELU, RESID, OUT_F32>(s, m, kp, grid);
+    case ACT_RELU: return launch_gemm_t<BN, ACT_RELU, RESID, OUT_F32>(s, m, kp, grid);
   }
   return cudaErrorInvalidValue;
 }
+
+template <int BN>
+cudaError_t launch_gemm_bn(cudaStream_t s, const Maps& m, const KParams& kp, int grid, int act, bool resid, bool out_f32) {
+  if (out_f32) return resid ? launch_gemm_act<BN, true, true>(s, m, kp, grid, act) : launch_gemm_act<BN, false, true>(s, m, kp, grid, act);
+  return resid ? launch_gemm_act<BN, true, false>(s, m, kp, grid, act) : launch_gemm_act<BN, false, false>(s, m, kp, grid, act);
+}
+
+}  // namespace
 
 cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, int ldb, void* Cout, int ldc, int M, int N,
                         int K, const GemmEpilogue& epi) {
@@ -323,9 +425,19 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   if ((K % 8) || (N % 8) || (lda % 8) || (ldb % 8) || (ldc % 8)) return cudaErrorInvalidValue;
   if (epi.resid != nullptr && (epi.ldr % 8)) return cudaErrorInvalidValue;
   const int BN = (N % 256 == 0) ? 256 : 128;
-  CUtensorMap ta, tb;
-  if (!make_tmap_2d_bf16(&ta, A, M, K, lda, BM, BK)) return cudaErrorUnknown;
-  if (!make_tmap_2d_bf16(&tb, Wt, N, K, ldb, BN, BK)) return cudaErrorUnknown;
+  Maps m;
+  if (!make_tmap_2d_bf16(&m.a, A, M, K, lda, BM, BK, 128)) return cudaErrorUnknown;
+  if (!make_tmap_2d_bf16(&m.b, Wt, N, K, ldb, BN, BK, 128)) return cudaErrorUnknown;
+  if (!epi.out_f32) {
+    if (!make_tmap_2d_bf16(&m.c, Cout, M, N, ldc, 32, 32, 64)) return cudaErrorUnknown;
+  } else {
+    m.c = m.a;
+  }
+  if (epi.resid != nullptr && !epi.out_f32) {
+    if (!make_tmap_2d_bf16(&m.r, epi.resid, M, N, epi.ldr, 32, 32, 64)) return cudaErrorUnknown;
+  } else {
+    m.r = m.a;
+  }
   KParams kp;
   kp.M = M; kp.N = N; kp.K = K;
   kp.C = Cout; kp.ldc = ldc;
@@ -336,8 +448,8 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   kp.resid = epi.resid; kp.ldr = epi.ldr;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (BN == 256) return launch_gemm_bn<256>(s, ta, tb, kp, grid, epi.act, epi.out_f32);
-  return launch_gemm_bn<128>(s, ta, tb, kp, grid, epi.act, epi.out_f32);
+  if (BN == 256) return launch_gemm_bn<256>(s, m, kp, grid, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
+  return launch_gemm_bn<128>(s, m, kp, grid, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
 }
 
 }  // namespace vp
