@@ -53,7 +53,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -62,9 +62,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -74,7 +74,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.15)]
+        for ln in (inside or [ln for _, ln in self.lines]):
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -191,13 +192,14 @@ def main():
     def step(i):
         return model(bufs[i % n_bufs])[0]
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(warmup):
         step(i)
     barrier()
     launches0 = model.kernel_launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_wall0 = time.time()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
@@ -205,7 +207,7 @@ def main():
     end.record()
     barrier()
     ms = start.elapsed_time(end)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     launches = model.kernel_launches - launches0
     t = torch.tensor([ms], device="cuda")
     if world > 1:

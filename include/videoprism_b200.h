@@ -128,7 +128,8 @@ VP_API int vp_layernorm(const void* x, int ldx, const float* gamma1, const float
                  const float* add_table, int add_div, int add_mod, int M, int D, void* stream);
 /* patches [BT*(H/p)*(W/p), ldo] bf16 from video [BT,H,W,3] fp32 */
 VP_API int vp_patchify(const float* video, void* out, int ldo, int BT, int H, int W, int p, void* stream);
-/* attention over a packed q|k|v buffer; see csrc/kernels.h AttnArgs for the row mapping */
+/* attention over a packed q|k|v buffer; see csrc/kernels.h AttnArgs for the row mapping.
+ * causal: bit 0 = causal mask; bit 1 = force the mma.sync kernel (tests: bypass the tcgen05 S=256 kernel) */
 VP_API int vp_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int num_seq, int S,
                  int group, int heads, int dh, float cap, const float* key_pad, int causal, void* stream);
 

@@ -194,7 +194,9 @@ def ref_attention(qkv, num_seq, S, group, heads, dh, cap, key_pad, causal):
 
 
 @pytest.mark.parametrize("num_seq,S,group,heads,dh,causal,pad", [
-    (8, 256, 1, 12, 64, 0, False),      # spatial stack
+    (8, 256, 1, 12, 64, 0, False),      # spatial stack (tcgen05 kernel)
+    (300, 256, 1, 12, 64, 0, False),    # spatial stack, more problems than SMs x stages (persistent loop, phases)
+    (8, 256, 1, 12, 64, 2, False),      # spatial stack, mma.sync kernel forced
     (2 * 256, 16, 256, 12, 64, 0, False),  # temporal stack: tubes strided by N=256
     (2 * 16, 8, 16, 2, 32, 0, True),    # temporal, T=8, dh=32, frame paddings
     (6, 65, 1, 12, 64, 1, True),        # text tower: causal + paddings, ragged S
@@ -208,6 +210,8 @@ def test_attention(L, num_seq, S, group, heads, dh, causal, pad):
     rows = num_seq * S
     qkv = torch.randn((rows, 3 * D), device="cuda", generator=g)
     qkv[:, :D] *= 1.5          # logits of a few units .. tens: exercises the tanh cap
+    if num_seq == 8 and S == 256:
+        qkv[:256, :D] *= 4     # first frame: |logits| well beyond cap/2 -> the MUFU.TANH slow path of the tcgen05 kernel
     qkv = qkv.bfloat16()
     key_pad = None
     if pad:
@@ -221,5 +225,5 @@ def test_attention(L, num_seq, S, group, heads, dh, causal, pad):
                         group, heads, dh, 50.0, _p(key_pad), causal, _stream())
     assert rc == 0
     torch.cuda.synchronize()
-    ref = ref_attention(qkv, num_seq, S, group, heads, dh, 50.0, key_pad, bool(causal))
+    ref = ref_attention(qkv, num_seq, S, group, heads, dh, 50.0, key_pad, bool(causal & 1))
     _close(out, ref, rtol=2e-2, atol=2e-2)

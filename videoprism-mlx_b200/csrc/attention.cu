@@ -306,9 +306,15 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const AttnArgs a, int t
 
 }  // namespace
 
+cudaError_t launch_attention_tcgen05(cudaStream_t s, const AttnArgs& a);
+
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (a.num_seq <= 0 || a.S <= 0) return cudaSuccess;
   if ((a.ld % 8) || (a.ldo % 8) || (a.dh != 64 && a.dh != 32) || a.group < 1) return cudaErrorInvalidValue;
+  if (!a.force_mma_sync) {
+    const cudaError_t e = launch_attention_tcgen05(s, a);   // S = 256, dh = 64, unmasked: the spatial stack
+    if (e != cudaErrorNotSupported) return e;
+  }
   if (a.S <= 16) {
     const int total = a.num_seq * a.heads;
     const int grid = (total + 3) / 4;

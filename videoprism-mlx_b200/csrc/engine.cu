@@ -831,7 +831,7 @@ int vp_attention(const void* q, const void* k, const void* v, int ld, void* out,
   vp::AttnArgs a;
   a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.ld = ld;
   a.out = static_cast<bf16*>(out); a.ldo = ldo; a.num_seq = num_seq; a.S = S; a.group = group; a.heads = heads; a.dh = dh;
-  a.cap = cap; a.key_pad = key_pad; a.causal = causal;
+  a.cap = cap; a.key_pad = key_pad; a.causal = causal & 1; a.force_mma_sync = (causal >> 1) & 1;
   return ck(vp::launch_attention(static_cast<cudaStream_t>(stream), a));
 }
 

@@ -60,6 +60,7 @@ struct AttnArgs {
   float cap = 0.f;
   const float* key_pad = nullptr;
   int causal = 0;
+  int force_mma_sync = 0;   // tests: bypass the tcgen05 kernel
 };
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a);
 
