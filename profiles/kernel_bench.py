@@ -1,0 +1,85 @@
+"""Per-kernel micro-benchmarks through the C ABI (CUDA events, isolated kernels, base-model shapes at B clips).
+
+    python profiles/kernel_bench.py [B] [model]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import videoprism_b200._lib as L
+
+lib = L.lib()
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+model = sys.argv[2] if len(sys.argv) > 2 else "base"
+D, H, F = (768, 12, 3072) if model == "base" else (1024, 16, 4096)
+T, N = 16, 256
+M = B * T * N
+st = int(torch.cuda.current_stream().cuda_stream)
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def gemm(Mm, Nn, Kk, act=0, resid=False):
+    A = (torch.randn((Mm, Kk), device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn((Nn, Kk), device="cuda") * 0.02).bfloat16()
+    bias = torch.zeros((Nn,), device="cuda")
+    C = torch.zeros((Mm, Nn), dtype=torch.bfloat16, device="cuda")
+    def f():
+        rc = lib.vp_gemm_bf16(A.data_ptr(), Kk, Wt.data_ptr(), Kk, C.data_ptr(), Nn, Mm, Nn, Kk, bias.data_ptr(), act,
+                              C.data_ptr() if resid else None, Nn if resid else 0, None, None, 0, 0, st)
+        assert rc == 0
+    ms = timeit(f)
+    return ms, 2.0 * Mm * Nn * Kk / ms / 1e9
+
+
+def attention(num_seq, S, group, force=0, qscale=0.2):
+    qkv = torch.randn((num_seq * S, 3 * D), device="cuda")
+    qkv[:, :D] *= qscale      # |logits| of a few units (fast path of the cap); qscale=1 gives |s| > cap/2 rows (MUFU.TANH path)
+    qkv = qkv.bfloat16()
+    out = torch.zeros((num_seq * S, D), dtype=torch.bfloat16, device="cuda")
+    def f():
+        rc = lib.vp_attention(qkv.data_ptr(), qkv.data_ptr() + 2 * D, qkv.data_ptr() + 4 * D, 3 * D, out.data_ptr(), D, num_seq, S, group, H, 64,
+                              50.0, None, force * 2, st)
+        assert rc == 0
+    ms = timeit(f)
+    return ms, 4.0 * S * S * 64 * H * num_seq / ms / 1e9
+
+
+def layernorm():
+    x = torch.randn((M, D), device="cuda").bfloat16()
+    y = torch.empty_like(x)
+    g = torch.ones((D,), device="cuda"); b = torch.zeros((D,), device="cuda")
+    def f():
+        assert lib.vp_layernorm(x.data_ptr(), D, g.data_ptr(), b.data_ptr(), y.data_ptr(), None, None, 1, 1, M, D, st) == 0
+    ms = timeit(f)
+    return ms, 2.0 * M * D * 2 / ms / 1e6
+
+
+print(f"B={B} model={model} M={M}")
+for name, args in [("QKV   ", (M, 3 * D, D, 0, False)), ("outprj", (M, D, D, 0, True)), ("FFN1  ", (M, F, D, 1, False)), ("FFN2  ", (M, D, F, 0, True))]:
+    ms, tf = gemm(*args)
+    print(f"gemm {name} {args[0]}x{args[1]}x{args[2]}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = attention(B * T, N, 1)
+print(f"attention spatial (tcgen05): {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = attention(B * T, N, 1, qscale=1.0)
+print(f"attention spatial (tcgen05, large logits -> tanh path): {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = attention(B * T, N, 1, force=1)
+print(f"attention spatial (mma.sync): {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = attention(B * N, T, N)
+print(f"attention temporal: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s   ({(4.0*M*D*2)/ms/1e6:.0f} GB/s algorithmic)")
+ms, gbs = layernorm()
+print(f"layernorm [{M},{D}]: {ms*1e3:8.1f} us  {gbs:7.0f} GB/s")

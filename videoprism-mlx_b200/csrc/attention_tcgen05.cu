@@ -33,8 +33,8 @@ namespace {
 constexpr int kTileBytes = 256 * 64 * 2;        // one of Q / K / V for a problem: 32 KB
 constexpr int kStageBytes = 3 * kTileBytes;     // 96 KB
 constexpr int kStages = 2;
-constexpr int kThreads = 384;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kThreads = 640;   // 4 control warps + 16 softmax warps
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128 + 4096 + 2048;   // + barriers + max/min and sum exchange
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcParams {
@@ -58,6 +58,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+
+// TMEM layout of one query tile (256 columns at `T`):
+//   scores S        : [0, 256)                     fp32, written by the S MMA
+//   P (keys 0..127) : [0, 64)    P (keys 128..255) : [128, 192)   bf16 pairs, each half written over score
+//                                                                 columns its own warp has already consumed
+//   O               : [64, 128)                    fp32, written by the PV MMA after both P halves are complete
 __global__ void __launch_bounds__(kThreads, 1)
 attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -71,9 +78,11 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   auto o_full = [&](int t) { return bar_base + 8u * (10 + t); };
   auto tmem_free = [&](int t) { return bar_base + 8u * (12 + t); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * 14;
+  const uint32_t xchg_base = bar_base + 128;   // float [2 tiles][2 halves][128 rows][2] max/min (4 KB) + [2][2][128] sums (2 KB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int n_it = (p.num_problems - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -87,9 +96,9 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(s_full(t), 1);
-      mbar_init(p_full(t), 4);
+      mbar_init(p_full(t), 8);
       mbar_init(o_full(t), 1);
-      mbar_init(tmem_free(t), 4);
+      mbar_init(tmem_free(t), 8);
     }
     fence_mbar_init();
   }
@@ -121,49 +130,59 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+    // -------------------------------------------------------------- MMA issuer (event driven)
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // B = V is MN-major (dh contiguous per key)
-      int it = 0;
-      for (int pr = blockIdx.x; pr < p.num_problems; pr += gridDim.x, ++it) {
-        const int stage = it & 1;
-        const uint32_t sphase = (it >> 1) & 1u;
-        const uint32_t tphase = it & 1u;
-        const uint32_t sq = smem_base + stage * kStageBytes;
-        const uint32_t sk = sq + kTileBytes, sv = sk + kTileBytes;
-        mbar_wait(full_qk(stage), sphase);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_kmajor_sw128(sk);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(tmem_free(t), tphase ^ 1u);   // previous problem's O of this tile has been read out
-          tc_fence_after();
-          const uint64_t dq = umma_desc_kmajor_sw128(sq + t * (kTileBytes / 2));
+      int s_it[2] = {0, 0}, pv_it[2] = {0, 0};
+      while (pv_it[0] < n_it || pv_it[1] < n_it) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(s_full(t));
-        }
-        mbar_wait(full_v(stage), sphase);
-        tc_fence_after();
-        // V tile: key k at byte k*128 (64 dh values), 8-key swizzle atoms of 1024 B; one K=16 step = 2 atoms
-        const uint64_t dv = umma_desc_mnmajor_sw128(sv, 1024, 1024);
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(p_full(t), tphase);
-          tc_fence_after();
+          const uint32_t T = tmem_base + t * 256;
+          if (s_it[t] < n_it && s_it[t] == pv_it[t]) {
+            // S(it) of this tile: needs Q,K of the stage and the tile's TMEM (previous O read out)
+            const int it = s_it[t];
+            const int stage = it & 1;
+            if (mbar_test(full_qk(stage), (it >> 1) & 1u) && mbar_test(tmem_free(t), (it & 1u) ^ 1u)) {
+              tc_fence_after();
+              const uint32_t sq = smem_base + stage * kStageBytes;
+              const uint64_t dq = umma_desc_kmajor_sw128(sq + t * (kTileBytes / 2));
+              const uint64_t dk = umma_desc_kmajor_sw128(sq + kTileBytes);
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 8 * k, dv + static_cast<uint64_t>(k) * (2048 >> 4),
-                         idesc_pv, k != 0 ? 1u : 0u);
-          umma_commit(o_full(t));
+              for (int k = 0; k < 4; ++k) umma_bf16_ss(T, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+              umma_commit(s_full(t));
+              s_it[t] = it + 1;
+            }
+          } else if (pv_it[t] < s_it[t]) {
+            const int it = pv_it[t];
+            const int stage = it & 1;
+            if (mbar_test(full_v(stage), (it >> 1) & 1u) && mbar_test(p_full(t), it & 1u)) {
+              tc_fence_after();
+              // V tile: key k at byte k*128 (64 dh values), 8-key swizzle atoms of 1024 B; one K=16 step = 2 atoms
+              const uint64_t dv = umma_desc_mnmajor_sw128(smem_base + stage * kStageBytes + 2 * kTileBytes, 1024, 1024);
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                umma_bf16_ts(T + 64, T + (k < 8 ? 8 * k : 128 + 8 * (k - 8)), dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv,
+                             k != 0 ? 1u : 0u);
+              umma_commit(o_full(t));
+              pv_it[t] = it + 1;
+            }
+          }
         }
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------------------- softmax warpgroups
-    const int tile = (warp - 4) >> 2;
+    // -------------------------------------------------------------- softmax warps: (tile, column half, lane quarter)
+    const int tile = (warp - 4) >> 3;
+    const int ch = ((warp - 4) >> 2) & 1;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;                       // row inside the 128-row query tile
-    const uint32_t t_s = tmem_base + tile * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t T = tmem_base + tile * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t t_s = T + ch * 128;                    // this warp's 128 score columns
+    const uint32_t xme = xchg_base + ((tile * 2 + ch) * 128 + row) * 8;
+    const uint32_t xpartner = xchg_base + ((tile * 2 + (ch ^ 1)) * 128 + row) * 8;
+    const uint32_t xsum_me = xchg_base + 4096 + ((tile * 2 + ch) * 128 + row) * 4;         // separate slots: no reuse hazard
+    const uint32_t xsum_partner = xchg_base + 4096 + ((tile * 2 + (ch ^ 1)) * 128 + row) * 4;
     const f32x2 B0 = pk2(p.b0, p.b0), B1 = pk2(p.b1, p.b1), B2 = pk2(p.b2, p.b2), B3 = pk2(p.b3, p.b3);
     int it = 0;
     for (int pr = blockIdx.x; pr < p.num_problems; pr += gridDim.x, ++it) {
@@ -172,10 +191,10 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       const int frame = pr / p.heads, h = pr % p.heads;
       mbar_wait(s_full(tile), tphase);
       tc_fence_after();
-      // ---- pass 1: row max / min of the raw logits (the cap is monotonic)
+      // ---- pass 1: max / min of the raw logits over this warp's half row, exchanged with the partner warp
       float mx = -CUDART_INF_F, mn = CUDART_INF_F;
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_s + 32 * j, r);
         tmem_ld_wait();
@@ -184,6 +203,14 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           mx = max3(mx, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           mn = min3(mn, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
         }
+      }
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xme), "f"(mx), "f"(mn) : "memory");
+      named_bar_sync(1 + tile, 256);
+      {
+        float pmx, pmn;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pmx), "=f"(pmn) : "r"(xpartner));
+        mx = fmaxf(mx, pmx);
+        mn = fminf(mn, pmn);
       }
       const bool fast = fmaxf(mx, -mn) <= p.range;
       float m_l2;
@@ -194,10 +221,10 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         m_l2 = p.cap_l2 * tanh_approx(mx * p.inv_cap);
       }
       const f32x2 negm = pk2(-m_l2, -m_l2);
-      // ---- pass 2: cap, exp2, row sum, bf16 P written over the dead score columns
+      // ---- pass 2: cap, exp2, partial row sum, bf16 P written over this warp's own dead score columns
       f32x2 sum2 = pk2(0.f, 0.f);
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_s + 32 * j, r);
         tmem_ld_wait();
@@ -226,22 +253,25 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             w[i] = pack_bf16x2(e0, e1);
           }
         }
-        tmem_st_32x32b_x16(t_s + 16 * j, w);   // P columns [16j, 16j+16): two bf16 per column, already consumed scores
+        tmem_st_32x32b_x16(t_s + 16 * j, w);   // keys [ch*128 + 32j, +32) -> P columns ch*128 + [16j, 16j+16)
       }
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(tile));
       float s0, s1;
       upk2(sum2, s0, s1);
-      const float inv = 1.0f / (s0 + s1);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum_me), "f"(s0 + s1) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(tile));
+      named_bar_sync(1 + tile, 256);
+      float psum;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(psum) : "r"(xsum_partner));
+      const float inv = 1.0f / (s0 + s1 + psum);
       const f32x2 inv2 = pk2(inv, inv);
-      // ---- O = P V is ready: normalise, stage in the dead Q tile, TMA store
+      // ---- O = P V is ready: this warp normalises output columns [32 ch, 32 ch + 32), stages them in the dead Q tile
       mbar_wait(o_full(tile), tphase);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32b_x32(t_s + 128, o0);
-      tmem_ld_32x32b_x32(t_s + 160, o1);
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(T + 64 + 32 * ch, o);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -250,29 +280,26 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       const uint32_t rowaddr = so + row * 128;
       const int sw = row & 7;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t wv[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const int idx = c * 8 + jj * 2;
-          const uint32_t lo = idx < 32 ? o0[idx] : o1[idx - 32];
-          const uint32_t hi = idx < 32 ? o0[idx + 1] : o1[idx - 31];
           float a, b;
-          upk2(mul2(pk2u(lo, hi), inv2), a, b);
+          upk2(mul2(pk2u(o[c * 8 + jj * 2], o[c * 8 + jj * 2 + 1]), inv2), a, b);
           wv[jj] = pack_bf16x2(a, b);
         }
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((c ^ sw) << 4)), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((4 * ch + c) ^ sw) << 4)), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
       }
       fence_proxy_async_smem();
-      named_bar_sync(1 + tile, 128);
-      if (wq == 0 && lane == 0) {
+      named_bar_sync(1 + tile, 256);
+      if (ch == 0 && wq == 0 && lane == 0) {
         tma_store_2d(&tmO, so, h * 64, frame * 256 + tile * 128);
         tma_store_commit();
         tma_store_wait_read<0>();
         mbar_arrive(empty(stage));   // Q/K/V of this stage are dead (both PV MMAs retired before o_full) and O has left smem
       }
     }
-    if (wq == 0 && lane == 0) tma_store_wait<0>();
+    if (ch == 0 && wq == 0 && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
