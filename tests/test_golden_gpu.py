@@ -1,0 +1,91 @@
+"""CUDA path (through the reference-facing surface / C ABI) vs the committed golden vectors produced by the
+reference's own module code (tests/golden/make_golden.py).  bf16 tolerance of BASELINE.json's north star:
+per-token cosine >= 0.999, max-abs reported."""
+import os
+
+import numpy as np
+import pytest
+
+import videoprism_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COS_MIN = 0.999
+
+
+def cos_min(a, b):
+    a = a.reshape(-1, a.shape[-1]).astype(np.float64); b = b.reshape(-1, b.shape[-1]).astype(np.float64)
+    return float(((a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1) + 1e-30)).min())
+
+
+def check(tag, got, want):
+    c = cos_min(got, want)
+    print(f"[golden] {tag}: min cosine {c:.6f}, max-abs {np.abs(got - want).max():.4g} (ref max {np.abs(want).max():.4g})")
+    assert c >= COS_MIN
+
+
+def model_for(cfg):
+    import videoprism_b200 as vp
+    cls = vp.FactorizedEncoder if cfg["kind"] == "encoder" else vp.FactorizedVideoCLIP
+    return cls(**{k: v for k, v in cfg.items() if k != "kind"})
+
+
+def test_tiny_encoder_cases():
+    g = np.load(os.path.join(G, "enc_tiny_interp.npz"))
+    cfg = O.tiny_config("encoder", pos_emb_shape=(16, 16, 16))
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 4, 16, seed=11, kind="normal")
+    m = model_for(cfg)
+    out, outs = m.apply(W, v, train=False, return_intermediate=True)
+    check("tiny encoder (tables down-sampled)", out, g["features"])
+    check("  spatial_features", outs["spatial_features"], g["spatial_features"])
+    outp, _ = m.apply(W, v, train=False, frame_paddings=g["frame_paddings"])
+    check("  with frame_paddings", outp, g["features_frame_paddings"])
+    g = np.load(os.path.join(G, "enc_tiny_upsample.npz"))
+    cfg = O.tiny_config("encoder")
+    out, _ = model_for(cfg).apply(O.make_synthetic_weights(cfg), O.make_video(2, 8, 32, seed=12, kind="normal"), train=False)
+    check("tiny encoder (tables up-sampled)", out, g["features"])
+
+
+def test_tiny_clip_case():
+    g = np.load(os.path.join(G, "clip_tiny.npz"))
+    cfg = O.tiny_config("clip")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(3, 4, 16, seed=13, kind="normal")
+    m = model_for(cfg)
+    ve, te, outs = m.apply(W, v, g["ids"], g["paddings"], train=False, return_intermediate=True)
+    check("tiny clip video_emb", ve, g["video_emb_norm"])
+    check("tiny clip text_emb", te, g["text_emb_norm"])
+    for k in ("spatial_features", "spatiotemporal_features", "frame_embeddings"):
+        check("  " + k, outs[k], g[k])
+    ve, te, _ = m.apply(W, v, g["ids"], g["paddings"], train=False, normalize=False)
+    check("tiny clip video_emb (raw)", ve, g["video_emb_raw"])
+    check("tiny clip text_emb (raw)", te, g["text_emb_raw"])
+
+
+@pytest.mark.parametrize("case,T,seed,kind", [("base_config1", 16, 0, "uniform"), ("base_T8", 8, 1, "normal")])
+def test_base_encoder_full_size(case, T, seed, kind):
+    import videoprism_b200 as vp
+    g = np.load(os.path.join(G, case + ".npz"))
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    m = vp.get_model("videoprism_public_v1_base")
+    out, _ = m.apply(O.make_synthetic_weights(cfg), O.make_video(1, T, 288, seed=seed, kind=kind), train=False)
+    check(case, out[:, :: int(g["token_stride"])], g["features_sample"])
+
+
+def test_lvt_base_one_clip_three_queries():
+    import videoprism_b200 as vp
+    g = np.load(os.path.join(G, "lvt_base_1clip_3text.npz"))
+    cfg = O.CONFIGS["videoprism_lvt_public_v1_base"]
+    m = vp.get_model("videoprism_lvt_public_v1_base")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(1, 16, 288, seed=0)
+    ve, te, _ = m.apply(W, v, g["ids"], g["paddings"], train=False)
+    check("lvt base video_emb", ve, g["video_emb"])
+    check("lvt base text_emb", te, g["text_emb"])
+    sim_err = np.abs(ve @ te.T - g["video_emb"] @ g["text_emb"].T).max()
+    print(f"[golden] lvt base similarity-matrix max-abs diff {sim_err:.4g}")
+    assert sim_err < 2e-2
+    ve, te, _ = m.apply(W, v, g["ids"], g["paddings"], train=False, normalize=False)
+    check("lvt base video_emb (raw)", ve, g["video_emb_raw"])
+    check("lvt base text_emb (raw)", te, g["text_emb_raw"])
