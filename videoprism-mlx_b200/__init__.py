@@ -8,7 +8,7 @@ without a B200 raises.
 from . import models  # noqa: F401
 from .models import (  # noqa: F401
     CONFIGS, MODELS, get_model, has_model, load_pretrained_weights, load_video_encoder, load_model,
-    FactorizedEncoder, FactorizedVideoCLIP, synthetic_state,
+    FactorizedEncoder, FactorizedVideoCLIP, synthetic_state, pinned_empty, compute_similarity_matrix,
 )
 
 __version__ = "0.1.0"

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -97,6 +98,11 @@ struct vp_handle {
 
   // workspace
   DevBuf ws_x, ws_n, ws_qkv, ws_u, ws_patch, ws_misc, ws_io_in, ws_io_out, ws_pool;
+  // host-buffer pipeline (vp_encoder_forward_host)
+  bool pipe_init = false;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
+  int host_chunk_clips = 0;   // 0 = automatic
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -557,6 +563,7 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
   }
   vp_handle* h = new vp_handle();
   h->cfg = *cfg;
+  if (const char* ev = getenv("VP_HOST_CHUNK_CLIPS")) h->host_chunk_clips = atoi(ev);   // tuning knob of the host pipeline
   cudaGetDevice(&h->device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, h->device);
@@ -583,6 +590,11 @@ void vp_destroy(vp_handle* h) {
   if (h->d_spatial_pos) cudaFree(h->d_spatial_pos);
   if (h->d_temporal_pos) cudaFree(h->d_temporal_pos);
   if (h->d_pe) cudaFree(h->d_pe);
+  if (h->pipe_init) {
+    cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_comp[i]); cudaEventDestroy(h->ev_out[i]); }
+    cudaEventDestroy(h->ev_start);
+  }
   DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool};
   for (DevBuf* b : bufs) b->release();
   delete h;
@@ -644,6 +656,9 @@ int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, in
                       out_dtype == VP_BF16 ? static_cast<bf16*>(out_features) : nullptr, false, static_cast<float*>(spatial_features), st, nullptr);
 }
 
+// Host-buffer entry point, software-pipelined over clip chunks: H2D of chunk i+1 (copy-in stream), forward of
+// chunk i (caller's stream) and D2H of chunk i-1 (copy-out stream) overlap; device staging is double buffered
+// and ordered with events.  Pinned host buffers give true DMA overlap; pageable ones still work (staged copies).
 int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
                             float* out_features, float* spatial_features, void* stream) {
   int rc = check_ready(h);
@@ -651,25 +666,60 @@ int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int 
   if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
   if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || H % h->cfg.patch_size || W % h->cfg.patch_size) return h->fail(VP_ERR_INVALID, "bad clip shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t in_elems = (size_t)B * T * H * W * 3;
+  if (!h->pipe_init) {
+    CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    h->pipe_init = true;
+  }
+  const size_t clip_in = (size_t)T * H * W * 3;
   const size_t N = (size_t)(H / h->cfg.patch_size) * (W / h->cfg.patch_size);
-  const size_t out_elems = (size_t)B * T * N * h->cfg.model_dim;
+  const size_t clip_out = (size_t)T * N * h->cfg.model_dim;
+  const int chunk = h->host_chunk_clips > 0 ? h->host_chunk_clips : (B >= 16 ? 8 : (B >= 4 ? (B + 1) / 2 : B));
+  const int nchunks = (B + chunk - 1) / chunk;
+  const size_t in_stride = ((size_t)chunk * clip_in * sizeof(float) + 255) / 256 * 256;
+  const size_t out_stride = ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256;
   const size_t pad_bytes = frame_paddings ? (size_t)B * T * sizeof(float) : 0;
-  CK(h->ws_io_in.ensure(in_elems * sizeof(float) + 256 + pad_bytes));
-  CK(h->ws_io_out.ensure(out_elems * sizeof(float) * (spatial_features ? 2 : 1)));
-  float* d_in = static_cast<float*>(h->ws_io_in.p);
+  CK(h->ws_io_in.ensure(2 * in_stride + 256 + pad_bytes));
+  CK(h->ws_io_out.ensure(2 * out_stride * (spatial_features ? 2 : 1)));
+  char* in_base = static_cast<char*>(h->ws_io_in.p);
+  char* out_base = static_cast<char*>(h->ws_io_out.p);
   float* d_pad = nullptr;
-  CK(cudaMemcpyAsync(d_in, video, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
   if (frame_paddings) {
-    d_pad = reinterpret_cast<float*>(reinterpret_cast<char*>(d_in) + ((in_elems * sizeof(float) + 255) / 256) * 256);
+    d_pad = reinterpret_cast<float*>(in_base + 2 * in_stride);
     CK(cudaMemcpyAsync(d_pad, frame_paddings, pad_bytes, cudaMemcpyHostToDevice, st));
   }
-  float* d_out = static_cast<float*>(h->ws_io_out.p);
-  float* d_sp = spatial_features ? d_out + out_elems : nullptr;
-  rc = encoder_body(h, d_in, B, T, H, W, d_pad, d_out, nullptr, false, d_sp, st, nullptr);
-  if (rc != VP_OK) return rc;
-  CK(cudaMemcpyAsync(out_features, d_out, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (spatial_features) CK(cudaMemcpyAsync(spatial_features, d_sp, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+  // the side streams start after whatever the caller already queued on `st`
+  CK(cudaEventRecord(h->ev_start, st));
+  CK(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  CK(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
+  for (int i = 0; i < nchunks; ++i) {
+    const int b = i & 1;
+    const int c0 = i * chunk;
+    const int bc = (B - c0) < chunk ? (B - c0) : chunk;
+    float* d_in = reinterpret_cast<float*>(in_base + b * in_stride);
+    float* d_out = reinterpret_cast<float*>(out_base + b * out_stride);
+    float* d_sp = spatial_features ? reinterpret_cast<float*>(out_base + (2 + b) * out_stride) : nullptr;
+    if (i >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));       // chunk i-2 no longer reads this input buffer
+    CK(cudaMemcpyAsync(d_in, video + (size_t)c0 * clip_in, (size_t)bc * clip_in * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+    CK(cudaEventRecord(h->ev_in[b], h->s_in));
+    CK(cudaStreamWaitEvent(st, h->ev_in[b], 0));
+    if (i >= 2) CK(cudaStreamWaitEvent(st, h->ev_out[b], 0));             // chunk i-2's D2H has drained this output buffer
+    rc = encoder_body(h, d_in, bc, T, H, W, d_pad ? d_pad + (size_t)c0 * T : nullptr, d_out, nullptr, false, d_sp, st, nullptr);
+    if (rc != VP_OK) { cudaDeviceSynchronize(); return rc; }
+    CK(cudaEventRecord(h->ev_comp[b], st));
+    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+    CK(cudaMemcpyAsync(out_features + (size_t)c0 * clip_out, d_out, (size_t)bc * clip_out * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (spatial_features)
+      CK(cudaMemcpyAsync(spatial_features + (size_t)c0 * clip_out, d_sp, (size_t)bc * clip_out * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    CK(cudaEventRecord(h->ev_out[b], h->s_out));
+  }
+  CK(cudaStreamSynchronize(h->s_out));
   CK(cudaStreamSynchronize(st));
   return VP_OK;
 }

@@ -197,7 +197,10 @@ class FactorizedEncoder(_Module):
 
     _kind = _lib.VP_KIND_ENCODER
 
-    def __call__(self, inputs, train: bool = False, return_intermediate: bool | Collection[str] = False, frame_paddings=None):
+    def __call__(self, inputs, train: bool = False, return_intermediate: bool | Collection[str] = False, frame_paddings=None,
+                 out=None):
+        """`out` (extension, host path only): a preallocated float32 C-contiguous `[B, T*N, D]` numpy array to receive
+        the features, e.g. from `pinned_empty` so the device-to-host copy is a true asynchronous DMA."""
         del train  # dropout probabilities are 0 in every released config: train has no effect on the forward
         lib = _lib.lib()
         h = self._ensure_handle()
@@ -222,7 +225,10 @@ class FactorizedEncoder(_Module):
             outs = {"spatial_features": sp} if want_spatial else {}
             return out, outs
         x = np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)
-        out = np.empty((b, t * n, d), dtype=np.float32)
+        if out is None:
+            out = np.empty((b, t * n, d), dtype=np.float32)
+        elif out.shape != (b, t * n, d) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a C-contiguous float32 array of shape {(b, t * n, d)}")
         sp = np.empty_like(out) if want_spatial else None
         fp = None if frame_paddings is None else np.ascontiguousarray(np.asarray(frame_paddings), dtype=np.float32)
         _lib.check(lib.vp_encoder_forward_host(
@@ -444,6 +450,19 @@ def load_model(model_name: str, weights_path: Optional[str] = None, state: Optio
         state = load_checkpoint(path)
     model.load_state(state)
     return model
+
+
+_PINNED_KEEPALIVE = {}
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A numpy array backed by page-locked host memory (cudaHostAlloc through torch): H2D / D2H copies of such
+    buffers are asynchronous DMAs, which is what lets the host entry points overlap copies with compute."""
+    import torch
+    t = torch.empty(tuple(shape), dtype={np.float32: torch.float32, np.int32: torch.int32}[np.dtype(dtype).type], pin_memory=True)
+    a = t.numpy()
+    _PINNED_KEEPALIVE[a.ctypes.data] = t
+    return a
 
 
 def compute_similarity_matrix(video_emb, text_emb):
