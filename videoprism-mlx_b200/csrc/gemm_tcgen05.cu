@@ -19,6 +19,7 @@
 // Replaces the reference's nn.Dense / einsum projections (layers.py:304-312, :486-488, :483-498).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -35,12 +36,15 @@ constexpr int kNumEpiWarps = 8;
 constexpr int kStageTileBytes = 32 * 32 * 2;            // one 32x32 bf16 staging tile
 constexpr int kStagingBytes = kNumEpiWarps * 2 * kStageTileBytes;  // 32 KB
 
-template <int BN>
+// CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BN tile; 2 = an SM pair per 256 x BN tile, each CTA holding
+// its 128 A rows and HALF of the B rows (BN/2), which halves the per-SM smem fill traffic and allows 6 stages.
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBRows = BN / CG;                      // B rows resident per CTA
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);   // 4 (48 KB) or 6 (32 KB)
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -60,11 +64,11 @@ struct KParams {
 
 __device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int ACT, bool RESID, bool OUT_F32>
+template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + C::kPipeBytes;
@@ -80,10 +84,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_tiles = (p.M + BM - 1) / BM;
+  constexpr int TM = BM * CG;                                  // rows of one (pair) tile
+  const int num_m_tiles = (p.M + TM - 1) / TM;
   const int num_n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile0 = static_cast<int>(blockIdx.x) / CG;         // first tile of this CTA (pair)
+  const int tile_step = static_cast<int>(gridDim.x) / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -98,7 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kNumEpiWarps);
+      mbar_init(tempty_bar(a), kNumEpiWarps * CG);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     for (int w = 0; w < kNumEpiWarps; ++w) {
       mbar_init(resid_bar(w, 0), 1);
@@ -106,9 +114,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_mbar_init();
   }
+  if (CG == 2) cluster_sync_all();   // barrier inits of both CTAs are visible before any remote arrive / multicast commit
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_addr, C::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(tmem_ptr_addr, C::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_addr, C::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -121,28 +130,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * BM;
-        const int n0 = (tile % num_n_tiles) * BN;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;            // this CTA's 128 A rows
+        const int n0 = (tile % num_n_tiles) * BN + cta_rank * C::kBRows;     // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + C::kABytes;
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
+          if (CG == 2) {
+            // both CTAs' bytes are credited to the leader's full barrier; only the leader arms it
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d_pair(sb, &tmB, full_bar(stage), kb * BK, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), C::kStageBytes);
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -158,12 +174,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (start address is in 16 B units)
-            umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_ss_pair(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CG == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (CG == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));  // accumulator complete
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -176,8 +194,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t stg = staging_base + e * 2 * kStageTileBytes;
     uint32_t rphase0 = 0, rphase1 = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / num_n_tiles) * BM;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;
       const int n0 = (tile % num_n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
@@ -214,7 +232,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // all TMEM reads of this warp for this tile are done: release the accumulator early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+          }
         }
         const int n = n0 + col;
         f32x2 v[16];
@@ -328,9 +348,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // no CTA of the pair exits (or frees TMEM) while its peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -388,33 +409,45 @@ struct Maps {
   CUtensorMap a, b, c, r;
 };
 
-template <int BN, int ACT, bool RESID, bool OUT_F32>
+template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp, int grid) {
-  auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32>;
+  auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32, CG>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  kern<<<grid, kNumThreads, Cfg<BN>::kSmemBytes, s>>>(m.a, m.b, m.c, m.r, kp);
-  return cudaGetLastError();
+  if (CG == 1) {
+    kern<<<grid, kNumThreads, Cfg<BN, CG>::kSmemBytes, s>>>(m.a, m.b, m.c, m.r, kp);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg<BN, CG>::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.c, m.r, kp);
 }
 
-template <int BN, bool RESID, bool OUT_F32>
+template <int BN, bool RESID, bool OUT_F32, int CG>
 cudaError_t launch_gemm_act(cudaStream_t s, const Maps& m, const KParams& kp, int grid, int act) {
   switch (act) {
-    case ACT_NONE: return launch_gemm_t<BN, ACT_NONE, RESID, OUT_F32>(s, m, kp, grid);
-    case ACT_GELU: return launch_gemm_t<BN, ACT_GELU, RESID, OUT_F32>(s, m, kp, grid);
-    case ACT_RELU: return launch_gemm_t<BN, ACT_RELU, RESID, OUT_F32>(s, m, kp, grid);
+    case ACT_NONE: return launch_gemm_t<BN, ACT_NONE, RESID, OUT_F32, CG>(s, m, kp, grid);
+    case ACT_GELU: return launch_gemm_t<BN, ACT_GELU, RESID, OUT_F32, CG>(s, m, kp, grid);
+    case ACT_RELU: return launch_gemm_t<BN, ACT_RELU, RESID, OUT_F32, CG>(s, m, kp, grid);
   }
   return cudaErrorInvalidValue;
 }
 
-template <int BN>
+template <int BN, int CG>
 cudaError_t launch_gemm_bn(cudaStream_t s, const Maps& m, const KParams& kp, int grid, int act, bool resid, bool out_f32) {
-  if (out_f32) return resid ? launch_gemm_act<BN, true, true>(s, m, kp, grid, act) : launch_gemm_act<BN, false, true>(s, m, kp, grid, act);
-  return resid ? launch_gemm_act<BN, true, false>(s, m, kp, grid, act) : launch_gemm_act<BN, false, false>(s, m, kp, grid, act);
+  if (out_f32) return resid ? launch_gemm_act<BN, true, true, CG>(s, m, kp, grid, act) : launch_gemm_act<BN, false, true, CG>(s, m, kp, grid, act);
+  return resid ? launch_gemm_act<BN, true, false, CG>(s, m, kp, grid, act) : launch_gemm_act<BN, false, false, CG>(s, m, kp, grid, act);
 }
 
 }  // namespace
@@ -425,9 +458,15 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   if ((K % 8) || (N % 8) || (lda % 8) || (ldb % 8) || (ldc % 8)) return cudaErrorInvalidValue;
   if (epi.resid != nullptr && (epi.ldr % 8)) return cudaErrorInvalidValue;
   const int BN = (N % 256 == 0) ? 256 : 128;
+  // SM pairs (cta_group::2, 256 x 256 tiles) when the problem has at least one pair-tile per pair of SMs
+  static const int force_cg = getenv("VP_GEMM_CTA_GROUP") ? atoi(getenv("VP_GEMM_CTA_GROUP")) : 0;
+  const int pair_tiles = ((M + 255) / 256) * (N / 256);
+  int CG = (BN == 256 && !epi.out_f32 && pair_tiles >= num_sms() / 2) ? 2 : 1;
+  if (force_cg == 1) CG = 1;
+  if (force_cg == 2 && BN == 256) CG = 2;
   Maps m;
   if (!make_tmap_2d_bf16(&m.a, A, M, K, lda, BM, BK, 128)) return cudaErrorUnknown;
-  if (!make_tmap_2d_bf16(&m.b, Wt, N, K, ldb, BN, BK, 128)) return cudaErrorUnknown;
+  if (!make_tmap_2d_bf16(&m.b, Wt, N, K, ldb, BN / CG, BK, 128)) return cudaErrorUnknown;
   if (!epi.out_f32) {
     if (!make_tmap_2d_bf16(&m.c, Cout, M, N, ldc, 32, 32, 64)) return cudaErrorUnknown;
   } else {
@@ -446,10 +485,14 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   kp.pos_table = epi.pos_table;
   kp.pos_period = epi.pos_period > 0 ? epi.pos_period : 1;
   kp.resid = epi.resid; kp.ldr = epi.ldr;
+  if (CG == 2) {
+    const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
+    return launch_gemm_bn<256, 2>(s, m, kp, 2 * pairs, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
+  }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (BN == 256) return launch_gemm_bn<256>(s, m, kp, grid, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
-  return launch_gemm_bn<128>(s, m, kp, grid, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
+  if (BN == 256) return launch_gemm_bn<256, 1>(s, m, kp, grid, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
+  return launch_gemm_bn<128, 1>(s, m, kp, grid, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
 }
 
 }  // namespace vp
