@@ -34,17 +34,19 @@ constexpr int kNumThreads = 384;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kNumEpiWarps = 8;
 constexpr int kStageTileBytes = 32 * 32 * 2;            // one 32x32 bf16 staging tile
-constexpr int kStagingBytes = kNumEpiWarps * 2 * kStageTileBytes;  // 32 KB
 
 // CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BN tile; 2 = an SM pair per 256 x BN tile, each CTA holding
 // its 128 A rows and HALF of the B rows (BN/2), which halves the per-SM smem fill traffic and allows 6 stages.
-template <int BN, int CG>
+// NBUF = staging tiles per epilogue warp: 2 (ping-pong), or 4 for the residual GEMMs on SM pairs, whose smaller
+// pipeline stages leave room to prefetch the residual tiles of all four column chunks at tile start.
+template <int BN, int CG, int NBUF>
 struct Cfg {
   static constexpr int kBRows = BN / CG;                      // B rows resident per CTA
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);   // 4 (48 KB) or 6 (32 KB)
+  static constexpr int kStagingBytes = kNumEpiWarps * NBUF * kStageTileBytes;               // 32 or 64 KB
+  static constexpr int kStages = ((229376 - kStagingBytes) / kStageBytes) > 8 ? 8 : ((229376 - kStagingBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -68,18 +70,19 @@ template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  using C = Cfg<BN, CG>;
+  constexpr int NBUF = (RESID && CG == 2 && !OUT_F32) ? 4 : 2;
+  using C = Cfg<BN, CG, NBUF>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + C::kPipeBytes;
-  const uint32_t bar_base = staging_base + kStagingBytes;
+  const uint32_t bar_base = staging_base + C::kStagingBytes;
   // barriers (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], resid[8 warps][2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  auto resid_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * 2 + b); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4 + 2 * kNumEpiWarps);
+  auto resid_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * NBUF + b); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4 + NBUF * kNumEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,10 +111,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kNumEpiWarps * CG);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
-    for (int w = 0; w < kNumEpiWarps; ++w) {
-      mbar_init(resid_bar(w, 0), 1);
-      mbar_init(resid_bar(w, 1), 1);
-    }
+    for (int w = 0; w < kNumEpiWarps; ++w)
+      for (int b = 0; b < NBUF; ++b) mbar_init(resid_bar(w, b), 1);
     fence_mbar_init();
   }
   if (CG == 2) cluster_sync_all();   // barrier inits of both CTAs are visible before any remote arrive / multicast commit
@@ -191,8 +192,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = e >> 2;         // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
     constexpr int NCH = kColsPerWarp / 32;
-    const uint32_t stg = staging_base + e * 2 * kStageTileBytes;
-    uint32_t rphase0 = 0, rphase1 = 0;
+    const uint32_t stg = staging_base + e * NBUF * kStageTileBytes;
+    uint32_t rphase = 0;   // bit b = parity of residual barrier b
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;
@@ -204,13 +205,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (RESID && !OUT_F32) {
         // prefetch the residual tiles of the first two chunks into the two staging buffers
         if (lane == 0) {
-          tma_store_wait_read<1>();   // the store that last used buffer 0 has drained
-          mbar_expect_tx(resid_bar(e, 0), kStageTileBytes);
-          tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
-          if (NCH > 1) {
-            tma_store_wait_read<0>();
+          if (NBUF == 4) {
+            // one buffer per column chunk: the previous tile's four stores were issued in buffer order
+            tma_store_wait_read<3>();
+            mbar_expect_tx(resid_bar(e, 0), kStageTileBytes);
+            tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
+            tma_store_wait_read<2>();
             mbar_expect_tx(resid_bar(e, 1), kStageTileBytes);
             tma_load_2d(stg + kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
+            tma_store_wait_read<1>();
+            mbar_expect_tx(resid_bar(e, 2), kStageTileBytes);
+            tma_load_2d(stg + 2 * kStageTileBytes, &tmR, resid_bar(e, 2), ncol0 + 64, mrow0);
+            tma_store_wait_read<0>();
+            mbar_expect_tx(resid_bar(e, 3), kStageTileBytes);
+            tma_load_2d(stg + 3 * kStageTileBytes, &tmR, resid_bar(e, 3), ncol0 + 96, mrow0);
+          } else {
+            tma_store_wait_read<1>();   // the store that last used buffer 0 has drained
+            mbar_expect_tx(resid_bar(e, 0), kStageTileBytes);
+            tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
+            if (NCH > 1) {
+              tma_store_wait_read<0>();
+              mbar_expect_tx(resid_bar(e, 1), kStageTileBytes);
+              tma_load_2d(stg + kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
+            }
           }
         }
       }
@@ -294,14 +311,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else {
-          const int b = ch & 1;
+          const int b = (NBUF == 4) ? ch : (ch & 1);
           const uint32_t buf = stg + b * kStageTileBytes;
           // 64-byte rows, 16-byte chunk c of row `lane` lives at chunk (c ^ ((lane >> 1) & 3))  (TMA SWIZZLE_64B)
           const uint32_t rowaddr = buf + lane * 64;
           const int sw = (lane >> 1) & 3;
           if (RESID) {
-            mbar_wait(resid_bar(e, b), b ? rphase1 : rphase0);
-            if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
+            mbar_wait(resid_bar(e, b), (rphase >> b) & 1u);
+            rphase ^= 1u << b;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t w0, w1, w2, w3;
@@ -331,7 +348,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) {
             tma_store_2d(&tmC, buf, n, mrow0);   // clipped against [M, N] by the tensor map
             tma_store_commit();
-            if (RESID && ch + 2 < NCH) {
+            if (RESID && NBUF == 2 && ch + 2 < NCH) {
               // buffer (ch+1)&1 ... is busy; the buffer for chunk ch+2 is this one: wait for the store just issued
               // to finish reading it, then prefetch that chunk's residual tile
               tma_store_wait_read<0>();
@@ -412,20 +429,21 @@ struct Maps {
 template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp, int grid) {
   auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32, CG>;
+  constexpr int kSmem = Cfg<BN, CG, (RESID && CG == 2 && !OUT_F32) ? 4 : 2>::kSmemBytes;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   if (CG == 1) {
-    kern<<<grid, kNumThreads, Cfg<BN, CG>::kSmemBytes, s>>>(m.a, m.b, m.c, m.r, kp);
+    kern<<<grid, kNumThreads, kSmem, s>>>(m.a, m.b, m.c, m.r, kp);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg<BN, CG>::kSmemBytes;
+  cfg.dynamicSmemBytes = kSmem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
