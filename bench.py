@@ -135,6 +135,74 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_retrieval(args):
+    """BASELINE.json configs[3]/[4]: videoprism_lvt_public_v1_{base,large}; clips and text queries sharded over the
+    ranks, pooled embeddings all-gathered (NCCL), similarity matrix [clips, queries] on every rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import videoprism_b200 as vp
+    from videoprism_b200.retrieval import retrieval_similarity, shard_range
+    name = {"base": "videoprism_lvt_public_v1_base", "large": "videoprism_lvt_public_v1_large"}[args.model]
+    model = vp.get_model(name)
+    model.load_state(vp.synthetic_state(model, seed=1234))
+    n_clips = args.global_batch if args.global_batch != 32 else 256
+    n_q = args.global_queries
+    lo, hi = shard_range(n_clips, rank, world)
+    qlo, qhi = shard_range(n_q, rank, world)
+    rng = np.random.default_rng(100 + rank)
+    video = torch.from_numpy(rng.random((hi - lo, 16, 288, 288, 3), dtype=np.float32)).cuda()
+    ids_all = np.random.default_rng(2).integers(1, 32000, (n_q, 64), dtype=np.int32)
+    lens = np.random.default_rng(3).integers(4, 33, (n_q,))
+    pad_all = (np.arange(64)[None, :] >= lens[:, None]).astype(np.float32)
+    ids_all = np.where(pad_all > 0, 0, ids_all).astype(np.int32)
+    ids = torch.from_numpy(ids_all[qlo:qhi]).cuda(); pad = torch.from_numpy(pad_all[qlo:qhi]).cuda()
+    warmup = max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        sim = retrieval_similarity(model, video, ids, pad)
+    barrier()
+    l0 = model.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sim = retrieval_similarity(model, video, ids, pad)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        gf = {"base": 1231.04 - 38.71 + 0.15, "large": 3410.92 - 68.80 + 0.27}[args.model]   # pooler in its executed (collapsed) form
+        gfq = {"base": 11.20, "large": 19.84}[args.model]
+        tf = (n_clips * gf + n_q * gfq) / ms / world   # GF/ms = TF/s per GPU
+        peaks, src = measured_peaks()
+        print(json.dumps({
+            "metric": "clips/sec (video-text retrieval step)", "value": n_clips / (ms / 1e3), "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{name}: {n_clips} clips x {n_q} text queries, all-gather of pooled embeddings, similarity matrix",
+                       "clips_per_gpu": hi - lo, "queries_per_gpu": qhi - qlo, "parallelism": f"dp{world} + all-gather (NCCL)"},
+            "queries_per_s": n_q / (ms / 1e3), "similarity_shape": list(sim.shape), "gpu_launches": int(model.kernel_launches - l0),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["bf16_tflops_sustained"], "peak_source": src, "traffic": None,
+                         "note": "whole step per GPU; algorithmic GF with the pooling head in its executed single-query form"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,11 +211,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="base", choices=["base", "large"])
     ap.add_argument("--global-batch", type=int, default=32)
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "retrieval"],
+                    help="encoder: BASELINE configs 2/3 (default); retrieval: configs 4/5 (LvT video+text, all-gather, similarity)")
+    ap.add_argument("--global-queries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "retrieval":
+        return run_retrieval(args)
 
     import numpy as np
     import torch

@@ -110,6 +110,53 @@ def test_base_encoder_parity_config1():
     assert m.kernel_launches > 0
 
 
+def test_large_encoder_parity_config3_shapes():
+    """BASELINE.json configs[2]: videoprism_public_v1_large (24+4 blocks, D=1024, H=16, F=4096); its temporal
+    table has 8 rows and is bilinearly resized to the 16 frames (encoders.py:551-552)."""
+    import videoprism_b200 as vp
+    name = "videoprism_public_v1_large"
+    cfg = O.CONFIGS[name]
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(1, 16, 288, seed=5)
+    want, _ = O.run_encoder(cfg, W, v)
+    m = vp.get_model(name)
+    got, _ = m.apply(W, v, train=False)
+    assert got.shape == (1, 4096, 1024)
+    c, _ = report("large encoder (config-3 model), 1 clip", got, want)
+    assert c >= COS_MIN
+
+
+def test_lvt_large_text_and_video_parity():
+    """videoprism_lvt_public_v1_large: text tower on 6 ragged queries + video side on 1 clip."""
+    import videoprism_b200 as vp
+    name = "videoprism_lvt_public_v1_large"
+    cfg = O.CONFIGS[name]
+    W = O.make_synthetic_weights(cfg)
+    ids, pad = O.make_text(6)
+    v = O.make_video(1, 16, 288, seed=6)
+    wv, wt, _ = O.run_clip(cfg, W, v, ids, pad)
+    m = vp.get_model(name)
+    gv, gt, _ = m.apply(W, v, ids, pad, train=False)
+    assert report("lvt large video emb", gv, wv)[0] >= COS_MIN
+    assert report("lvt large text emb", gt, wt)[0] >= COS_MIN
+
+
+def test_batched_forward_matches_single_clip_forward():
+    """Clips are independent (encoders.py:434-436): a B=5 forward equals five B=1 forwards bit for bit, and the
+    chunk-pipelined host entry point equals the device entry point."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    m = vp.get_model("videoprism_public_v1_base")
+    m.load_state(O.make_synthetic_weights(cfg))
+    v = O.make_video(5, 16, 288, seed=8)
+    full, _ = m(v)
+    dev, _ = m(torch.from_numpy(v).cuda())
+    assert np.array_equal(dev.cpu().numpy(), full)
+    for b in (0, 4):
+        one, _ = m(v[b:b + 1])
+        assert np.array_equal(one[0], full[b])
+
+
 def test_errors_mirror_reference():
     cfg = O.tiny_config("encoder")
     m = make_model(cfg)
