@@ -242,6 +242,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
         const int col = half * kColsPerWarp + ch * 32;
+        // bias for this chunk is fetched before the TMEM load so the two latencies overlap
+        float4 bv[8];
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            bv[g] = (n0 + col + g * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + col + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
@@ -260,11 +267,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.bias != nullptr) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            if (n + g * 4 < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + g * 4));
-              v[2 * g] = add2(v[2 * g], pk2(b.x, b.y));
-              v[2 * g + 1] = add2(v[2 * g + 1], pk2(b.z, b.w));
-            }
+            v[2 * g] = add2(v[2 * g], pk2(bv[g].x, bv[g].y));
+            v[2 * g + 1] = add2(v[2 * g + 1], pk2(bv[g].z, bv[g].w));
           }
         }
         if (ACT == ACT_GELU) {
