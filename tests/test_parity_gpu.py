@@ -157,6 +157,37 @@ def test_batched_forward_matches_single_clip_forward():
         assert np.array_equal(one[0], full[b])
 
 
+@pytest.mark.parametrize("B,T,size", [(3, 16, 216), (2, 5, 288), (1, 1, 288), (7, 16, 144)])
+def test_base_encoder_ragged_shapes(B, T, size):
+    """Shapes off the benchmark grid on the full-size base model: other resolutions (position table resized,
+    S = 144 / 64 tokens per frame -> the generic attention kernel), odd frame counts (temporal table resized,
+    T = 1: single-key softmax), batch sizes that do not fill a GEMM tile."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(B, T, size, seed=20 + B)
+    want, _ = O.run_encoder(cfg, W, v)
+    m = vp.get_model("videoprism_public_v1_base")
+    got, _ = m.apply(W, v, train=False)
+    assert got.shape == want.shape
+    assert report(f"base encoder B={B} T={T} {size}x{size}", got, want)[0] >= COS_MIN
+
+
+def test_base_encoder_frame_paddings_full_size():
+    """frame_paddings on the full-size model: padded frames are masked as keys in the temporal stack, padded
+    frames attend uniformly in the spatial stack, and FFN outputs of padded tokens are zeroed (layers.py:397-411)."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 16, 288, seed=31)
+    fp = np.zeros((2, 16), np.float32)
+    fp[0, 10:] = 1
+    fp[1, ::4] = 1
+    want, _ = O.run_encoder(cfg, W, v, frame_paddings=torch.from_numpy(fp))
+    got, _ = vp.get_model("videoprism_public_v1_base").apply(W, v, train=False, frame_paddings=fp)
+    assert report("base encoder + frame_paddings", got, want)[0] >= COS_MIN
+
+
 def test_errors_mirror_reference():
     cfg = O.tiny_config("encoder")
     m = make_model(cfg)
