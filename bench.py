@@ -312,6 +312,20 @@ def main():
                "d2h_bytes_per_step": out_bytes, "steps": n_e2e,
                "how": "models.FactorizedEncoder.__call__(numpy, out=pinned) -> vp_encoder_forward_host: per step H2D of the clips, forward, D2H of the features (chunk-pipelined over 3 streams), wall clock, max over ranks"}
 
+        # same call fed with uint8 frames (as decoded; the /255 of video_utils.load_video runs on the device): 4x smaller H2D
+        u8 = torch.randint(0, 256, (b_local, T, S, S, 3), dtype=torch.uint8).pin_memory().numpy()
+        model(u8, out=host_out)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            model(u8, out=host_out)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["uint8_frames"] = {"value": args.global_batch * n_e2e / float(tt.item()), "unit": "clips/s",
+                               "h2d_bytes_per_step": b_local * clip_bytes // 4, "d2h_bytes_per_step": out_bytes}
+
     # ---- roofline of the dominant kernel (FFN1 GEMM + GELU epilogue), CUDA events on the launch stream
     peaks, peak_src = measured_peaks()
     roof = None

@@ -38,7 +38,7 @@ typedef enum vp_status {
   VP_ERR_UNSUPPORTED = -5
 } vp_status;
 
-typedef enum vp_dtype { VP_F32 = 0, VP_BF16 = 1, VP_I32 = 2 } vp_dtype;
+typedef enum vp_dtype { VP_F32 = 0, VP_BF16 = 1, VP_I32 = 2, VP_U8 = 3 } vp_dtype;
 
 typedef enum vp_model_kind {
   VP_KIND_ENCODER = 0, /* encoders.FactorizedEncoder   (videoprism/encoders.py:391-580) */
@@ -92,6 +92,14 @@ VP_API int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, in
  * the features, one stream synchronisation at the end.  Outputs are fp32. */
 VP_API int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
                             float* out_features, float* spatial_features, void* stream);
+
+/* Same two calls for uint8 frames [B,T,H,W,3] (0..255) as cv2 decodes them: the `astype(float32) / 255.0` of
+ * video_utils.load_video (videoprism/video_utils.py:88-93) happens on the device inside the patchify kernel,
+ * bit-identically, so the host-to-device copy is 4x smaller. */
+VP_API int vp_encoder_forward_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
+                          void* out_features, void* spatial_features, int out_dtype, void* stream);
+VP_API int vp_encoder_forward_host_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
+                               float* out_features, float* spatial_features, void* stream);
 
 /* -- FactorizedVideoCLIP.__call__ (videoprism/encoders.py:784-910), video side:
  *    vision_encoder -> auxiliary_encoder -> contrastive_vision_pooler -> (l2 normalise).

@@ -188,6 +188,21 @@ def test_base_encoder_frame_paddings_full_size():
     assert report("base encoder + frame_paddings", got, want)[0] >= COS_MIN
 
 
+def test_uint8_frames_match_float_frames_bitwise():
+    """uint8 frames (what cv2 decodes) take the /255 on the device: identical to feeding
+    `frames.astype(float32) / 255.0` (video_utils.py:88-93), on the host and the device entry points."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    m = vp.get_model("videoprism_public_v1_base")
+    m.load_state(O.make_synthetic_weights(cfg))
+    u8 = np.random.default_rng(3).integers(0, 256, (3, 16, 288, 288, 3), dtype=np.uint8)
+    f32 = u8.astype(np.float32) / 255.0
+    a, _ = m(f32)
+    b, _ = m(u8)
+    c, _ = m(torch.from_numpy(u8).cuda())
+    assert np.array_equal(a, b) and np.array_equal(a, c.cpu().numpy())
+
+
 def test_errors_mirror_reference():
     cfg = O.tiny_config("encoder")
     m = make_model(cfg)

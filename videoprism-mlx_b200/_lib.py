@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvideoprism_b200.so")
 
 VP_OK, VP_ERR_INVALID, VP_ERR_KEY, VP_ERR_INCOMPLETE, VP_ERR_CUDA, VP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-VP_F32, VP_BF16, VP_I32 = 0, 1, 2
+VP_F32, VP_BF16, VP_I32, VP_U8 = 0, 1, 2, 3
 VP_KIND_ENCODER, VP_KIND_CLIP = 0, 1
 
 
@@ -36,6 +36,8 @@ _PROTOS = {
     "vp_finalize": (_I, [_P]),
     "vp_encoder_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "vp_encoder_forward_host": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "vp_encoder_forward_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "vp_encoder_forward_host_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "vp_clip_video_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "vp_clip_text_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "vp_clip_video_forward_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),

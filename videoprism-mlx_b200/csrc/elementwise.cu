@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 // ------------------------------------------------------------------- patchify
 // One thread per pair of adjacent output elements: the (px, c) run of a patch row is 3p
 // contiguous floats in the source frame (p even => float2 / bf16x2 aligned).
-__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ video, bf16* __restrict__ out, int ldo,
+template <typename TIn>
+__global__ void __launch_bounds__(256) patchify_kernel(const TIn* __restrict__ video, bf16* __restrict__ out, int ldo,
                                                        int BT, int H, int W, int p, long long total_pairs) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total_pairs) return;
@@ -108,7 +109,13 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   const int gy = static_cast<int>(t % gh); t /= gh;
   const long long bt = t;
   const size_t src = ((static_cast<size_t>(bt) * H + (gy * p + py)) * W + gx * p) * 3 + 2 * j;
-  const float2 v = *reinterpret_cast<const float2*>(video + src);
+  float2 v;
+  if (sizeof(TIn) == 1) {
+    const uchar2 u = *reinterpret_cast<const uchar2*>(video + src);
+    v = make_float2(__fdiv_rn(static_cast<float>(u.x), 255.0f), __fdiv_rn(static_cast<float>(u.y), 255.0f));
+  } else {
+    v = *reinterpret_cast<const float2*>(video + src);
+  }
   const size_t row = (static_cast<size_t>(bt) * gh + gy) * gw + gx;
   const size_t dst = row * ldo + static_cast<size_t>(py) * 3 * p + 2 * j;
   *reinterpret_cast<uint32_t*>(out + dst) = pack_bf16x2(v.x, v.y);
@@ -204,7 +211,17 @@ cudaError_t launch_patchify(cudaStream_t s, const float* video, bf16* out, int l
   if (total == 0) return cudaSuccess;
   const int block = 256;
   const long long grid = (total + block - 1) / block;
-  patchify_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(video, out, ldo, BT, H, W, p, total);
+  patchify_kernel<float><<<static_cast<unsigned>(grid), block, 0, s>>>(video, out, ldo, BT, H, W, p, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_patchify_u8(cudaStream_t s, const uint8_t* video, bf16* out, int ldo, int BT, int H, int W, int p) {
+  if ((p % 2) || (H % p) || (W % p) || (ldo % 2)) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(BT) * (H / p) * (W / p) * p * (3 * p / 2);
+  if (total == 0) return cudaSuccess;
+  const int block = 256;
+  const long long grid = (total + block - 1) / block;
+  patchify_kernel<uint8_t><<<static_cast<unsigned>(grid), block, 0, s>>>(video, out, ldo, BT, H, W, p, total);
   return cudaGetLastError();
 }
 

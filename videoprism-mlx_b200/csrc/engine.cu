@@ -486,7 +486,7 @@ int check_ready(vp_handle* h) {
 
 // Shared body of the encoder forward.  Leaves the final (pre-temporal_ln) residual stream in ws_x and
 // writes LN outputs where requested.  Returns the token count through *M_out.
-int encoder_body(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
+int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
                  bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
   const vp_config& c = h->cfg;
   const int D = c.model_dim, P = c.patch_size;
@@ -512,7 +512,9 @@ int encoder_body(vp_handle* h, const float* video, int B, int T, int H, int W, c
   }
 
   // patchify + cast (encoders.py:436-439), patch projection + spatial pos-emb (:488-514)
-  CK(vp::launch_patchify(st, video, patches, h->k_patch_pad, B * T, H, W, P)); h->launches++;
+  if (in_dtype == VP_U8) CK(vp::launch_patchify_u8(st, static_cast<const uint8_t*>(video), patches, h->k_patch_pad, B * T, H, W, P));
+  else CK(vp::launch_patchify(st, static_cast<const float*>(video), patches, h->k_patch_pad, B * T, H, W, P));
+  h->launches++;
   vp::GemmEpilogue ep;
   ep.bias = h->b_patch; ep.pos_table = h->d_spatial_pos; ep.pos_period = N;
   CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->launches++;
@@ -644,23 +646,35 @@ int vp_finalize(vp_handle* h) {
   return VP_OK;
 }
 
-int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
-                       void* out_features, void* spatial_features, int out_dtype, void* stream) {
+static int encoder_forward_dev(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                               void* out_features, void* spatial_features, int out_dtype, void* stream) {
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
   if (out_dtype != VP_F32 && out_dtype != VP_BF16) return h->fail(VP_ERR_INVALID, "out_dtype must be VP_F32 or VP_BF16");
   if (spatial_features != nullptr && out_dtype != VP_F32) return h->fail(VP_ERR_UNSUPPORTED, "spatial_features requires VP_F32 outputs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return encoder_body(h, video, B, T, H, W, frame_paddings, out_dtype == VP_F32 ? static_cast<float*>(out_features) : nullptr,
+  return encoder_body(h, video, in_dtype, B, T, H, W, frame_paddings, out_dtype == VP_F32 ? static_cast<float*>(out_features) : nullptr,
                       out_dtype == VP_BF16 ? static_cast<bf16*>(out_features) : nullptr, false, static_cast<float*>(spatial_features), st, nullptr);
+}
+
+int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                       void* out_features, void* spatial_features, int out_dtype, void* stream) {
+  return encoder_forward_dev(h, video, VP_F32, B, T, H, W, frame_paddings, out_features, spatial_features, out_dtype, stream);
+}
+
+int vp_encoder_forward_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
+                          void* out_features, void* spatial_features, int out_dtype, void* stream) {
+  return encoder_forward_dev(h, video, VP_U8, B, T, H, W, frame_paddings, out_features, spatial_features, out_dtype, stream);
 }
 
 // Host-buffer entry point, software-pipelined over clip chunks: H2D of chunk i+1 (copy-in stream), forward of
 // chunk i (caller's stream) and D2H of chunk i-1 (copy-out stream) overlap; device staging is double buffered
 // and ordered with events.  Pinned host buffers give true DMA overlap; pageable ones still work (staged copies).
-int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
-                            float* out_features, float* spatial_features, void* stream) {
+static int encoder_forward_host_impl(vp_handle* h, const void* video_v, int in_dtype, int B, int T, int H, int W,
+                                     const float* frame_paddings, float* out_features, float* spatial_features, void* stream) {
+  const char* video = static_cast<const char*>(video_v);
+  const size_t esz = in_dtype == VP_U8 ? 1 : sizeof(float);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
@@ -682,7 +696,7 @@ int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int 
   const size_t clip_out = (size_t)T * N * h->cfg.model_dim;
   const int chunk = h->host_chunk_clips > 0 ? h->host_chunk_clips : (B >= 16 ? 8 : (B >= 4 ? (B + 1) / 2 : B));
   const int nchunks = (B + chunk - 1) / chunk;
-  const size_t in_stride = ((size_t)chunk * clip_in * sizeof(float) + 255) / 256 * 256;
+  const size_t in_stride = ((size_t)chunk * clip_in * esz + 255) / 256 * 256;
   const size_t out_stride = ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256;
   const size_t pad_bytes = frame_paddings ? (size_t)B * T * sizeof(float) : 0;
   CK(h->ws_io_in.ensure(2 * in_stride + 256 + pad_bytes));
@@ -706,11 +720,11 @@ int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int 
     float* d_out = reinterpret_cast<float*>(out_base + b * out_stride);
     float* d_sp = spatial_features ? reinterpret_cast<float*>(out_base + (2 + b) * out_stride) : nullptr;
     if (i >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));       // chunk i-2 no longer reads this input buffer
-    CK(cudaMemcpyAsync(d_in, video + (size_t)c0 * clip_in, (size_t)bc * clip_in * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+    CK(cudaMemcpyAsync(d_in, video + (size_t)c0 * clip_in * esz, (size_t)bc * clip_in * esz, cudaMemcpyHostToDevice, h->s_in));
     CK(cudaEventRecord(h->ev_in[b], h->s_in));
     CK(cudaStreamWaitEvent(st, h->ev_in[b], 0));
     if (i >= 2) CK(cudaStreamWaitEvent(st, h->ev_out[b], 0));             // chunk i-2's D2H has drained this output buffer
-    rc = encoder_body(h, d_in, bc, T, H, W, d_pad ? d_pad + (size_t)c0 * T : nullptr, d_out, nullptr, false, d_sp, st, nullptr);
+    rc = encoder_body(h, d_in, in_dtype, bc, T, H, W, d_pad ? d_pad + (size_t)c0 * T : nullptr, d_out, nullptr, false, d_sp, st, nullptr);
     if (rc != VP_OK) { cudaDeviceSynchronize(); return rc; }
     CK(cudaEventRecord(h->ev_comp[b], st));
     CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
@@ -722,6 +736,16 @@ int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int 
   CK(cudaStreamSynchronize(h->s_out));
   CK(cudaStreamSynchronize(st));
   return VP_OK;
+}
+
+int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                            float* out_features, float* spatial_features, void* stream) {
+  return encoder_forward_host_impl(h, video, VP_F32, B, T, H, W, frame_paddings, out_features, spatial_features, stream);
+}
+
+int vp_encoder_forward_host_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
+                               float* out_features, float* spatial_features, void* stream) {
+  return encoder_forward_host_impl(h, video, VP_U8, B, T, H, W, frame_paddings, out_features, spatial_features, stream);
 }
 
 int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
@@ -737,7 +761,7 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   size_t M = 0;
   // vision_encoder (encoders.py:822-841).  Its output (after temporal_ln) becomes the residual
   // stream of the auxiliary encoder, so LN writes bf16 back into ws_x.
-  rc = encoder_body(h, video, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
+  rc = encoder_body(h, video, VP_F32, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
   if (rc != VP_OK) return rc;
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   const int N = (int)(M / ((size_t)B * T));

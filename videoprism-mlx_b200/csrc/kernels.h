@@ -45,6 +45,8 @@ cudaError_t launch_layernorm(cudaStream_t s, const LnArgs& a);
 // Patchify + cast (encoders.py:70-104): video [BT, H, W, 3] fp32 -> patches [BT*(H/p)*(W/p), ldo] bf16,
 // column (py*p + px)*3 + c.  Columns >= p*p*3 are left untouched (zeroed once by the engine).
 cudaError_t launch_patchify(cudaStream_t s, const float* video, bf16* out, int ldo, int BT, int H, int W, int p);
+// same for uint8 frames: value / 255.0f in fp32 first, exactly as video_utils.load_video does (video_utils.py:88-93)
+cudaError_t launch_patchify_u8(cudaStream_t s, const uint8_t* video, bf16* out, int ldo, int BT, int H, int W, int p);
 
 // Attention over sequences embedded in a packed qkv buffer [rows, ld] (q at col q_off + h*dh, ...).
 // Sequence `sid` token j lives at row (sid / group) * (group * S) + (sid % group) + j * group.

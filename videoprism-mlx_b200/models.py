@@ -214,24 +214,28 @@ class FactorizedEncoder(_Module):
             import torch
             if not inputs.is_cuda:
                 raise ValueError("torch inputs must live on a CUDA device (pass numpy arrays for host buffers)")
-            x = inputs.to(torch.float32).contiguous()
+            is_u8 = inputs.dtype == torch.uint8     # raw decoded frames: / 255 happens on the device (video_utils.py:88-93)
+            x = inputs.contiguous() if is_u8 else inputs.to(torch.float32).contiguous()
+            fwd = lib.vp_encoder_forward_u8 if is_u8 else lib.vp_encoder_forward
             out = torch.empty((b, t * n, d), dtype=torch.float32, device=x.device)
             sp = torch.empty_like(out) if want_spatial else None
             fp = None if frame_paddings is None else torch.as_tensor(frame_paddings, device=x.device).to(torch.float32).contiguous()
             with torch.cuda.device(x.device):
-                _lib.check(lib.vp_encoder_forward(h, x.data_ptr(), b, t, hh, ww, None if fp is None else fp.data_ptr(),
+                _lib.check(fwd(h, x.data_ptr(), b, t, hh, ww, None if fp is None else fp.data_ptr(),
                                                   out.data_ptr(), None if sp is None else sp.data_ptr(), _lib.VP_F32,
                                                   self._stream_ptr()), h)
             outs = {"spatial_features": sp} if want_spatial else {}
             return out, outs
-        x = np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)
+        is_u8 = np.asarray(inputs).dtype == np.uint8
+        x = np.ascontiguousarray(np.asarray(inputs), dtype=np.uint8 if is_u8 else np.float32)
+        fwd_host = lib.vp_encoder_forward_host_u8 if is_u8 else lib.vp_encoder_forward_host
         if out is None:
             out = np.empty((b, t * n, d), dtype=np.float32)
         elif out.shape != (b, t * n, d) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
             raise ValueError(f"out must be a C-contiguous float32 array of shape {(b, t * n, d)}")
         sp = np.empty_like(out) if want_spatial else None
         fp = None if frame_paddings is None else np.ascontiguousarray(np.asarray(frame_paddings), dtype=np.float32)
-        _lib.check(lib.vp_encoder_forward_host(
+        _lib.check(fwd_host(
             h, x.ctypes.data_as(C.c_void_p), b, t, hh, ww, None if fp is None else fp.ctypes.data_as(C.c_void_p),
             out.ctypes.data_as(C.c_void_p), None if sp is None else sp.ctypes.data_as(C.c_void_p), None), h)
         outs = {"spatial_features": sp} if want_spatial else {}
