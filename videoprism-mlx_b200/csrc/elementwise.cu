@@ -5,6 +5,8 @@
 
 namespace vp {
 
+int num_sms();
+
 namespace {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -14,111 +16,143 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------ LayerNorm
-// One warp per row; the row (D bf16, D % 8 == 0, D <= 8 * 32 * VPL) is held in registers as
-// VPL 16-byte vectors per lane.  Two-pass statistics in fp32 (mean, then biased variance of the
-// centred values) as layers.py:240-242 does.
+// Persistent warps: each warp walks rows with a grid stride, holding one row (D bf16, D % 8 == 0,
+// D <= 8 * 32 * VPL) in registers as VPL 16-byte vectors per lane, and prefetches its next row before reducing the
+// current one; gamma / beta stay in registers.  Two-pass statistics in fp32 (mean, then biased variance of the centred values) as
+// layers.py:240-242 does.  Streaming loads / stores bypass L1.
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   const int warps_per_block = blockDim.x >> 5;
-  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= a.M) return;
   const int nvec = a.D >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(a.x + static_cast<size_t>(row) * a.ldx);
-  float v[VPL][8];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const uint4 u = xr[vi];
-      v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
-      v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
-    }
-  }
+  const int stride = gridDim.x * warps_per_block;
+  int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= a.M) return;
   const float inv_d = 1.0f / static_cast<float>(a.D);
-  const float mean = warp_sum(s) * inv_d;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    if (lane + i * 32 < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        sq += d * d;
-      }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-6f);
-  const float* addrow = nullptr;
-  if (a.add_table != nullptr) addrow = a.add_table + static_cast<size_t>((row / a.add_div) % a.add_mod) * a.D;
+  // gamma / beta of this lane's columns stay in registers for all rows
+  float4 g0[VPL], g1[VPL], b0[VPL], b1[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       const int c = vi * 8;
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma1 + c));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma1 + c + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c + 4));
-      float y[8];
-      y[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; y[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
-      y[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; y[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
-      y[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; y[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
-      y[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; y[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
-      if (a.y_f32 != nullptr) {
-        float* yp = a.y_f32 + static_cast<size_t>(row) * a.D + c;
-        *reinterpret_cast<float4*>(yp) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(yp + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      g0[i] = __ldg(reinterpret_cast<const float4*>(a.gamma1 + c)); g1[i] = __ldg(reinterpret_cast<const float4*>(a.gamma1 + c + 4));
+      b0[i] = __ldg(reinterpret_cast<const float4*>(a.beta + c)); b1[i] = __ldg(reinterpret_cast<const float4*>(a.beta + c + 4));
+    }
+  }
+  uint4 nxt[VPL];
+  {
+    const uint4* xr = reinterpret_cast<const uint4*>(a.x + static_cast<size_t>(row) * a.ldx);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + i * 32 < nvec) nxt[i] = ld_stream(xr + lane + i * 32);
+  }
+  for (; row < a.M; row += stride) {
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + i * 32 < nvec) {
+        const uint4 u = nxt[i];
+        v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
+        v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
       }
-      if (a.y_bf16 != nullptr) {
-        if (addrow != nullptr) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(addrow + c));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(addrow + c + 4));
-          y[0] += t0.x; y[1] += t0.y; y[2] += t0.z; y[3] += t0.w;
-          y[4] += t1.x; y[5] += t1.y; y[6] += t1.z; y[7] += t1.w;
+    }
+    // prefetch the next row of this warp while this one is reduced and written
+    if (row + stride < a.M) {
+      const uint4* xr = reinterpret_cast<const uint4*>(a.x + static_cast<size_t>(row + stride) * a.ldx);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + i * 32 < nvec) nxt[i] = ld_stream(xr + lane + i * 32);
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + i * 32 < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          sq += d * d;
         }
-        uint4 o;
-        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-        o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-        *reinterpret_cast<uint4*>(a.y_bf16 + static_cast<size_t>(row) * a.D + c) = o;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-6f);
+    const float* addrow = nullptr;
+    if (a.add_table != nullptr) addrow = a.add_table + static_cast<size_t>((row / a.add_div) % a.add_mod) * a.D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const int c = vi * 8;
+        float y[8];
+        y[0] = (v[i][0] - mean) * rstd * g0[i].x + b0[i].x; y[1] = (v[i][1] - mean) * rstd * g0[i].y + b0[i].y;
+        y[2] = (v[i][2] - mean) * rstd * g0[i].z + b0[i].z; y[3] = (v[i][3] - mean) * rstd * g0[i].w + b0[i].w;
+        y[4] = (v[i][4] - mean) * rstd * g1[i].x + b1[i].x; y[5] = (v[i][5] - mean) * rstd * g1[i].y + b1[i].y;
+        y[6] = (v[i][6] - mean) * rstd * g1[i].z + b1[i].z; y[7] = (v[i][7] - mean) * rstd * g1[i].w + b1[i].w;
+        if (a.y_f32 != nullptr) {
+          float* yp = a.y_f32 + static_cast<size_t>(row) * a.D + c;
+          *reinterpret_cast<float4*>(yp) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(yp + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        if (a.y_bf16 != nullptr) {
+          if (addrow != nullptr) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(addrow + c));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(addrow + c + 4));
+            y[0] += t0.x; y[1] += t0.y; y[2] += t0.z; y[3] += t0.w;
+            y[4] += t1.x; y[5] += t1.y; y[6] += t1.z; y[7] += t1.w;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+          o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(a.y_bf16 + static_cast<size_t>(row) * a.D + c) = o;
+        }
       }
     }
   }
 }
 
 // ------------------------------------------------------------------- patchify
-// One thread per pair of adjacent output elements: the (px, c) run of a patch row is 3p
-// contiguous floats in the source frame (p even => float2 / bf16x2 aligned).
+// One block per row of patches (bt, gy): p image rows of W*3 contiguous values each (fully coalesced pair loads);
+// value pair e of image row py lands in patch gx = e / (3p) at column py*3p + (e mod 3p): a 3p-element (108-byte)
+// contiguous run of the output row.  (p even => pairs never straddle patches.)
 template <typename TIn>
-__global__ void __launch_bounds__(256) patchify_kernel(const TIn* __restrict__ video, bf16* __restrict__ out, int ldo,
-                                                       int BT, int H, int W, int p, long long total_pairs) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total_pairs) return;
-  const int run = 3 * p / 2;  // float2 pairs per (patch, py)
-  const int gw = W / p, gh = H / p;
-  const int j = static_cast<int>(idx % run);
-  long long t = idx / run;
-  const int py = static_cast<int>(t % p);  t /= p;
-  const int gx = static_cast<int>(t % gw); t /= gw;
-  const int gy = static_cast<int>(t % gh); t /= gh;
-  const long long bt = t;
-  const size_t src = ((static_cast<size_t>(bt) * H + (gy * p + py)) * W + gx * p) * 3 + 2 * j;
-  float2 v;
-  if (sizeof(TIn) == 1) {
-    const uchar2 u = *reinterpret_cast<const uchar2*>(video + src);
-    v = make_float2(__fdiv_rn(static_cast<float>(u.x), 255.0f), __fdiv_rn(static_cast<float>(u.y), 255.0f));
-  } else {
-    v = *reinterpret_cast<const float2*>(video + src);
+__global__ void __launch_bounds__(448) patchify_kernel(const TIn* __restrict__ video, bf16* __restrict__ out, int ldo,
+                                                       int H, int W, int p) {
+  const int gh = H / p, gw = W / p;
+  const int gy = blockIdx.x % gh;
+  const size_t bt = blockIdx.x / gh;
+  const int run = 3 * p;                 // values per (patch, py)
+  const int row_vals = W * 3;
+  const TIn* src0 = video + (bt * H + static_cast<size_t>(gy) * p) * row_vals;
+  bf16* dst0 = out + ((bt * gh + gy) * gw) * static_cast<size_t>(ldo);
+  for (int t = threadIdx.x; 2 * t < row_vals; t += blockDim.x) {
+    const int e = 2 * t;
+    const int gx = e / run, j = e - gx * run;
+    bf16* dst = dst0 + static_cast<size_t>(gx) * ldo + j;
+#pragma unroll 6
+    for (int py = 0; py < p; ++py) {
+      float2 v;
+      if (sizeof(TIn) == 1) {
+        const uchar2 u = *reinterpret_cast<const uchar2*>(src0 + static_cast<size_t>(py) * row_vals + e);
+        v = make_float2(__fdiv_rn(static_cast<float>(u.x), 255.0f), __fdiv_rn(static_cast<float>(u.y), 255.0f));
+      } else {
+        v = *reinterpret_cast<const float2*>(src0 + static_cast<size_t>(py) * row_vals + e);
+      }
+      *reinterpret_cast<uint32_t*>(dst + py * run) = pack_bf16x2(v.x, v.y);
+    }
   }
-  const size_t row = (static_cast<size_t>(bt) * gh + gy) * gw + gx;
-  const size_t dst = row * ldo + static_cast<size_t>(py) * 3 * p + 2 * j;
-  *reinterpret_cast<uint32_t*>(out + dst) = pack_bf16x2(v.x, v.y);
 }
 
 // -------------------------------------------------------------- weight repack
@@ -192,7 +226,9 @@ cudaError_t launch_layernorm(cudaStream_t s, const LnArgs& a) {
   if (a.M <= 0) return cudaSuccess;
   if ((a.D % 8) || (a.ldx % 8) || a.D > 8 * 32 * 6) return cudaErrorInvalidValue;
   const int warps = 8;
-  const int grid = (a.M + warps - 1) / warps;
+  const int full = (a.M + warps - 1) / warps;
+  const int cap = num_sms() * 8;                       // persistent: up to 8 blocks of 8 warps per SM
+  const int grid = full < cap ? full : cap;
   const int nvec = a.D / 8;
   const int vpl = (nvec + 31) / 32;
   switch (vpl) {
@@ -207,21 +243,17 @@ cudaError_t launch_layernorm(cudaStream_t s, const LnArgs& a) {
 
 cudaError_t launch_patchify(cudaStream_t s, const float* video, bf16* out, int ldo, int BT, int H, int W, int p) {
   if ((p % 2) || (H % p) || (W % p) || (ldo % 2)) return cudaErrorInvalidValue;
-  const long long total = static_cast<long long>(BT) * (H / p) * (W / p) * p * (3 * p / 2);
-  if (total == 0) return cudaSuccess;
-  const int block = 256;
-  const long long grid = (total + block - 1) / block;
-  patchify_kernel<float><<<static_cast<unsigned>(grid), block, 0, s>>>(video, out, ldo, BT, H, W, p, total);
+  if (BT <= 0) return cudaSuccess;
+  const int block = (W * 3 / 2 >= 448) ? 448 : ((W * 3 / 2 + 31) / 32) * 32;
+  patchify_kernel<float><<<static_cast<unsigned>(BT) * (H / p), block, 0, s>>>(video, out, ldo, H, W, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_patchify_u8(cudaStream_t s, const uint8_t* video, bf16* out, int ldo, int BT, int H, int W, int p) {
   if ((p % 2) || (H % p) || (W % p) || (ldo % 2)) return cudaErrorInvalidValue;
-  const long long total = static_cast<long long>(BT) * (H / p) * (W / p) * p * (3 * p / 2);
-  if (total == 0) return cudaSuccess;
-  const int block = 256;
-  const long long grid = (total + block - 1) / block;
-  patchify_kernel<uint8_t><<<static_cast<unsigned>(grid), block, 0, s>>>(video, out, ldo, BT, H, W, p, total);
+  if (BT <= 0) return cudaSuccess;
+  const int block = (W * 3 / 2 >= 448) ? 448 : ((W * 3 / 2 + 31) / 32) * 32;
+  patchify_kernel<uint8_t><<<static_cast<unsigned>(BT) * (H / p), block, 0, s>>>(video, out, ldo, H, W, p);
   return cudaGetLastError();
 }
 
