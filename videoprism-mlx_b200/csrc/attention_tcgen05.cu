@@ -239,18 +239,21 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             q = fma2(q, u, B0);
             float a, b;
             upk2(fma2(q, v, negm), a, b);
-            const float e0 = ex2_approx(a), e1 = ex2_approx(b);
-            sum2 = add2(sum2, pk2(e0, e1));
-            w[i] = pack_bf16x2(e0, e1);
+            // P is truncated to bf16 with integer ops (ALU pipe) instead of cvt.rn.bf16x2 (F2FP shares the MUFU pipe
+            // with ex2 and was ~1/3 of its load); the row sum is taken over the TRUNCATED values, so the weights the
+            // tensor core sees sum to exactly the normaliser.
+            const uint32_t e0 = __float_as_uint(ex2_approx(a)) & 0xFFFF0000u, e1 = __float_as_uint(ex2_approx(b)) & 0xFFFF0000u;
+            sum2 = add2(sum2, pk2u(e0, e1));
+            w[i] = __byte_perm(e0, e1, 0x7632);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a = fmaf(p.cap_l2, tanh_approx(__uint_as_float(r[2 * i]) * p.inv_cap), -m_l2);
             const float b = fmaf(p.cap_l2, tanh_approx(__uint_as_float(r[2 * i + 1]) * p.inv_cap), -m_l2);
-            const float e0 = ex2_approx(a), e1 = ex2_approx(b);
-            sum2 = add2(sum2, pk2(e0, e1));
-            w[i] = pack_bf16x2(e0, e1);
+            const uint32_t e0 = __float_as_uint(ex2_approx(a)) & 0xFFFF0000u, e1 = __float_as_uint(ex2_approx(b)) & 0xFFFF0000u;
+            sum2 = add2(sum2, pk2u(e0, e1));
+            w[i] = __byte_perm(e0, e1, 0x7632);
           }
         }
         tmem_st_32x32b_x16(t_s + 16 * j, w);   // keys [ch*128 + 32j, +32) -> P columns ch*128 + [16j, 16j+16)
