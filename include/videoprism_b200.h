@@ -131,6 +131,20 @@ VP_API int vp_device_sm_count(void);                    /* < 0 when no CUDA devi
 VP_API int vp_gemm_bf16(const void* A, int lda, const void* Wt, int ldb, void* C, int ldc, int M, int N, int K,
                  const float* bias, int act, const void* resid, int ldr, const float* row_scale,
                  const float* pos_table, int pos_period, int out_f32, void* stream);
+/* LayerNorm folded into a projection (how the engine runs every LN -> Dense pair of a Transformer block,
+ * layers.py:822,:391 + :486-488,:304-312):  A holds RAW rows, Wt = (gamma1 (.) W)^T from vp_fold_ln_weight, and the
+ * epilogue applies  rstd[m]*acc - rstd[m]*mean[m]*ln_colsum[n] + bias[n]  from per-row partial (sum, sum of
+ * squares) ln_stats_in [M][ln_slots][2] (added in slot order).  stats_out (optional, [M][vp_gemm_stats_slots(N)][2])
+ * receives the same partial statistics of the stored bf16 output rows, one slot per (column tile, epilogue half),
+ * each written once: deterministic, no atomics. */
+VP_API int vp_gemm_bf16_ln(const void* A, int lda, const void* Wt, int ldb, void* C, int ldc, int M, int N, int K,
+                    const float* bias, int act, const void* resid, int ldr, const float* ln_stats_in, int ln_slots,
+                    const float* ln_colsum, int ln_dim, float* stats_out, void* stream);
+VP_API int vp_gemm_stats_slots(int N);
+VP_API int vp_row_stats(const void* x, int ldx, float* stats, int M, int D, void* stream);
+/* dst bf16 [N, ldk] = (gamma1[k] * src[k,n] * scale)^T ; colsum[n] = sum_k dst[n,k] ; bias_out = beta.src*scale + bias_in*scale */
+VP_API int vp_fold_ln_weight(const float* src, const float* gamma1, const float* beta, const float* bias_in, void* dst,
+                      float* colsum, float* bias_out, int K, int N, int ldk, float scale, void* stream);
 /* y = LayerNorm(x) * gamma1 + beta over the last dim, x bf16 [M,D]; y_bf16 / y_f32 may each be NULL. */
 VP_API int vp_layernorm(const void* x, int ldx, const float* gamma1, const float* beta, void* y_bf16, float* y_f32,
                  const float* add_table, int add_div, int add_mod, int M, int D, void* stream);

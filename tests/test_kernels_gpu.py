@@ -119,6 +119,42 @@ def test_gelu_epilogue_accuracy(L):
     assert (err / want.abs().clamp_min(2 ** -8)).max().item() < 8e-3  # ~2 bf16 ulps relative, abs 3e-5 near zero
 
 
+@pytest.mark.parametrize("M,D,N,mean_shift", [(1000, 768, 2304, 0.0), (777, 768, 3072, 3.0), (300, 64, 192, 1.0)])
+def test_layernorm_folded_into_gemm(L, M, D, N, mean_shift):
+    """LN -> Dense as ONE GEMM on the raw rows: weights (1+scale)(.)W, epilogue rstd*acc - rstd*mean*colsum + (beta.W + b)
+    (layers.py:237-270 followed by :304-312), plus the row statistics a residual GEMM emits for the next folded GEMM.
+    mean_shift puts a large common offset on the rows (|mean| = 3 sigma): the cancellation case of the fold."""
+    g = torch.Generator(device="cuda").manual_seed(N + D)
+    x = (torch.randn((M, D), device="cuda", generator=g) + mean_shift).bfloat16()
+    W = torch.randn((D, N), device="cuda", generator=g) * 0.05
+    b = torch.randn((N,), device="cuda", generator=g) * 0.1
+    gamma1 = 1 + 0.1 * torch.randn((D,), device="cuda", generator=g)
+    beta = 0.1 * torch.randn((D,), device="cuda", generator=g)
+    Wt = torch.empty((N, D), dtype=torch.bfloat16, device="cuda")
+    colsum = torch.empty((N,), device="cuda"); bias2 = torch.empty((N,), device="cuda")
+    assert L.vp_fold_ln_weight(W.data_ptr(), gamma1.data_ptr(), beta.data_ptr(), b.data_ptr(), Wt.data_ptr(), colsum.data_ptr(),
+                               bias2.data_ptr(), D, N, D, 1.0, _stream()) == 0
+    stats = torch.empty((M, 2), device="cuda")
+    assert L.vp_row_stats(x.data_ptr(), D, stats.data_ptr(), M, D, _stream()) == 0
+    torch.cuda.synchronize()
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.sum(-1), rtol=1e-5, atol=1e-3) and torch.allclose(stats[:, 1], (xf * xf).sum(-1), rtol=1e-5)
+    assert torch.allclose(colsum, Wt.float().sum(-1), rtol=1e-5, atol=1e-4)
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    slots = L.vp_gemm_stats_slots(N)
+    stats_out = torch.full((M, slots, 2), float("nan"), device="cuda")   # every slot must be written exactly once
+    assert L.vp_gemm_bf16_ln(x.data_ptr(), D, Wt.data_ptr(), D, out.data_ptr(), N, M, N, D, bias2.data_ptr(), 0, None, 0,
+                             stats.data_ptr(), 1, colsum.data_ptr(), D, stats_out.data_ptr(), _stream()) == 0
+    torch.cuda.synchronize()
+    mu = xf.mean(-1, keepdim=True)
+    var = ((xf - mu) ** 2).mean(-1, keepdim=True)
+    ref = ((xf - mu) * torch.rsqrt(var + 1e-6) * gamma1 + beta) @ W + b
+    _close(out, ref, rtol=2e-2, atol=3e-2 * (1 + mean_shift))
+    of = out.float()
+    assert torch.allclose(stats_out[:, :, 0].sum(1), of.sum(-1), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(stats_out[:, :, 1].sum(1), (of * of).sum(-1), rtol=1e-4, atol=1e-2)
+
+
 def test_gemm_strided_operands(L):
     # A is a column slice of a wider buffer (lda > K), as q|k|v slices are
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -47,6 +47,10 @@ _PROTOS = {
     "vp_kernel_launches": (C.c_int64, [_P]),
     "vp_device_sm_count": (_I, []),
     "vp_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
+    "vp_gemm_bf16_ln": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P]),
+    "vp_gemm_stats_slots": (_I, [_I]),
+    "vp_row_stats": (_I, [_P, _I, _P, _I, _I, _P]),
+    "vp_fold_ln_weight": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.c_float, _P]),
     "vp_layernorm": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vp_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "vp_attention": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.c_float, _P, _I, _P]),

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
     const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-6f);
     const float* addrow = nullptr;
     if (a.add_table != nullptr) addrow = a.add_table + static_cast<size_t>((row / a.add_div) % a.add_mod) * a.D;
+    float os = 0.f, oq = 0.f;   // statistics of the stored bf16 row (for the next LayerNorm-folded GEMM)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + i * 32;
@@ -117,8 +118,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
           o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
           o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
           *reinterpret_cast<uint4*>(a.y_bf16 + static_cast<size_t>(row) * a.D + c) = o;
+          if (a.stats_out != nullptr) {
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float lo = bf16_lo(ow[j]), hi = bf16_hi(ow[j]);
+              os += lo + hi;
+              oq = fmaf(lo, lo, fmaf(hi, hi, oq));
+            }
+          }
         }
       }
+    }
+    if (a.stats_out != nullptr) {
+      os = warp_sum(os); oq = warp_sum(oq);
+      if (lane == 0) { a.stats_out[2 * static_cast<size_t>(row)] = os; a.stats_out[2 * static_cast<size_t>(row) + 1] = oq; }
     }
   }
 }
@@ -178,6 +192,61 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 __global__ void affine_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, float a, float b) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = a * src[i] + b;
+}
+
+// ------------------------------------------------------------------ row stats
+__global__ void __launch_bounds__(256) row_stats_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ stats, int M, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
+  float s = 0.f, q = 0.f;
+  for (int vi = lane; vi < (D >> 3); vi += 32) {
+    const uint4 u = xr[vi];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+      s += lo + hi;
+      q = fmaf(lo, lo, fmaf(hi, hi, q));
+    }
+  }
+  s = warp_sum(s); q = warp_sum(q);
+  if (lane == 0) { stats[2 * static_cast<size_t>(row)] = s; stats[2 * static_cast<size_t>(row) + 1] = q; }
+}
+
+// ------------------------------------------------------- LayerNorm weight folding (load time)
+// One block per output feature n: dst[n, k] = bf16(gamma1[k] * src[k, n] * scale); colsum / bias reductions in fp32.
+__global__ void __launch_bounds__(256) fold_ln_weight_kernel(const float* __restrict__ src, const float* __restrict__ gamma1,
+                                                             const float* __restrict__ beta, const float* __restrict__ bias_in,
+                                                             bf16* __restrict__ dst, float* __restrict__ colsum,
+                                                             float* __restrict__ bias_out, int K, int N, int ldk, float scale) {
+  __shared__ float red[2][8];
+  const int n = blockIdx.x;
+  float cs = 0.f, bs = 0.f;
+  for (int k = threadIdx.x; k < ldk; k += blockDim.x) {
+    float wq = 0.f;
+    if (k < K) {
+      const float w = src[static_cast<size_t>(k) * N + n] * scale;
+      const bf16 wb = __float2bfloat16(w * gamma1[k]);
+      wq = __bfloat162float(wb);
+      bs += beta[k] * w;
+      dst[static_cast<size_t>(n) * ldk + k] = wb;
+    } else {
+      dst[static_cast<size_t>(n) * ldk + k] = __float2bfloat16(0.f);
+    }
+    cs += wq;
+  }
+  cs = warp_sum(cs); bs = warp_sum(bs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = cs; red[1][warp] = bs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f, b = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { c += red[0][w]; b += red[1][w]; }
+    colsum[n] = c;
+    bias_out[n] = b + (bias_in != nullptr ? bias_in[n] * scale : 0.f);
+  }
 }
 
 // ------------------------------------------------------------------- l2 norm
@@ -272,6 +341,19 @@ cudaError_t launch_cast_bf16(cudaStream_t s, const float* src, bf16* dst, size_t
 cudaError_t launch_affine_f32(cudaStream_t s, const float* src, float* dst, size_t n, float a, float b) {
   if (n == 0) return cudaSuccess;
   affine_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, dst, n, a, b);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_stats(cudaStream_t s, const bf16* x, int ldx, float* stats, int M, int D) {
+  if (M <= 0) return cudaSuccess;
+  if ((D % 8) || (ldx % 8)) return cudaErrorInvalidValue;
+  row_stats_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ldx, stats, M, D);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold_ln_weight(cudaStream_t s, const float* src, const float* gamma1, const float* beta, const float* bias_in,
+                                  bf16* dst, float* colsum, float* bias_out, int K, int N, int ldk, float scale) {
+  fold_ln_weight_kernel<<<N, 256, 0, s>>>(src, gamma1, beta, bias_in, dst, colsum, bias_out, K, N, ldk, scale);
   return cudaGetLastError();
 }
 

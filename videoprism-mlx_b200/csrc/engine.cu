@@ -59,6 +59,11 @@ struct StackWeights {
   bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  // LayerNorm folded into the QKV / FFN1 projections (see GemmEpilogue::ln_stats_in): (gamma1 (.) W)^T in bf16,
+  // column sums of the rounded weights, and beta.W + b; built by finalize_stack from the fp32 staging copies below.
+  bf16 *wqkv_ln = nullptr, *w1_ln = nullptr;
+  float *c1_qkv = nullptr, *c2_qkv = nullptr, *c1_ffn1 = nullptr, *c2_ffn1 = nullptr;
+  float *f_wqkv = nullptr, *f_bqkv = nullptr, *f_w1 = nullptr, *f_b1 = nullptr;   // fp32 [L][3][D][D], [L][3][D], [L][D][F], [L][F] (unscaled)
 };
 
 struct ParamSpec {
@@ -87,6 +92,8 @@ struct vp_handle {
   float* d_spatial_pos = nullptr; int spatial_grid_h = 0, spatial_grid_w = 0;
   float* d_temporal_pos = nullptr; int temporal_len = 0;
   StackWeights spatial, temporal, aux, text;
+  std::vector<StackWeights*> stacks;   // the stacks this model has (for finalize_stack)
+  bool fuse_ln = true;                 // LayerNorm folded into the QKV / FFN1 GEMMs (VP_FUSE_LN=0 disables)
   float *sp_ln_g = nullptr, *sp_ln_b = nullptr, *tp_ln_g = nullptr, *tp_ln_b = nullptr;
   // pooler (collapsed single-query form, see finalize_pooler)
   std::vector<float> h_pool_query, h_pool_wq, h_pool_bq, h_pool_wk, h_pool_pds;
@@ -97,7 +104,7 @@ struct vp_handle {
   float *uni_ln_g = nullptr, *uni_ln_b = nullptr;
 
   // workspace
-  DevBuf ws_x, ws_n, ws_qkv, ws_u, ws_patch, ws_misc, ws_io_in, ws_io_out, ws_pool;
+  DevBuf ws_x, ws_n, ws_qkv, ws_u, ws_patch, ws_misc, ws_io_in, ws_io_out, ws_pool, ws_stats;
   // host-buffer pipeline (vp_encoder_forward_host)
   bool pipe_init = false;
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -163,6 +170,19 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
   if ((e = dev_alloc(h, &w->ln1_b, (size_t)L * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &w->ln2_g, (size_t)L * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &w->ln2_b, (size_t)L * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->wqkv_ln, (size_t)L * 3 * D * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->w1_ln, (size_t)L * F * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->c1_qkv, (size_t)L * 3 * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->c2_qkv, (size_t)L * 3 * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->c1_ffn1, (size_t)L * F)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->c2_ffn1, (size_t)L * F)) != cudaSuccess) return e;
+  // fp32 copies of the projections that get a LayerNorm folded in; kept for the life of the handle so that
+  // vp_finalize can re-fold after any later vp_set_weight (LN scale / bias and the kernels arrive in any order)
+  if ((e = dev_alloc(h, &w->f_wqkv, (size_t)L * 3 * D * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->f_bqkv, (size_t)L * 3 * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->f_w1, (size_t)L * D * F)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &w->f_b1, (size_t)L * F)) != cudaSuccess) return e;
+  h->stacks.push_back(w);
   const std::string p = prefix + "/x_layers";
   // query scale dh^-0.5 (layers.py:569-584, internal_enable_per_dim_scale=False) is folded into Wq, bq.
   const float qscale = 1.0f / sqrtf(static_cast<float>(dh));
@@ -179,12 +199,20 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
         cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * D * D, ww.wqkv + (size_t)l * 3 * D * D + (size_t)i * D * D,
                                                   D, D, D, sc);
         if (e != cudaSuccess) return e;
+        if (ww.f_wqkv != nullptr) {
+          e = copy_f32(s + (size_t)l * D * D, ww.f_wqkv + ((size_t)l * 3 + i) * D * D, (size_t)D * D, st);
+          if (e != cudaSuccess) return e;
+        }
       }
       return cudaSuccess; });
     add_spec(h, p + "/self_attention/" + names[i] + "/b", {L, H, dh}, [ww, L, D, i, sc](const float* s, cudaStream_t st) {
       for (int l = 0; l < L; ++l) {
         cudaError_t e = vp::launch_affine_f32(st, s + (size_t)l * D, ww.bqkv + (size_t)l * 3 * D + (size_t)i * D, D, sc, 0.f);
         if (e != cudaSuccess) return e;
+        if (ww.f_bqkv != nullptr) {
+          e = copy_f32(s + (size_t)l * D, ww.f_bqkv + ((size_t)l * 3 + i) * D, D, st);
+          if (e != cudaSuccess) return e;
+        }
       }
       return cudaSuccess; });
   }
@@ -202,9 +230,11 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
       cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * D * F, ww.w1 + (size_t)l * F * D, D, F, D, 1.0f);
       if (e != cudaSuccess) return e;
     }
-    return cudaSuccess; });
+    return ww.f_w1 != nullptr ? copy_f32(s, ww.f_w1, (size_t)L * D * F, st) : cudaSuccess; });
   add_spec(h, p + "/ff_layer/ffn_layer1/linear/bias", {L, F}, [ww, L, F](const float* s, cudaStream_t st) {
-    return copy_f32(s, ww.b1, (size_t)L * F, st); });
+    cudaError_t e = copy_f32(s, ww.b1, (size_t)L * F, st);
+    if (e != cudaSuccess) return e;
+    return ww.f_b1 != nullptr ? copy_f32(s, ww.f_b1, (size_t)L * F, st) : cudaSuccess; });
   add_spec(h, p + "/ff_layer/ffn_layer2/linear/kernel", {L, F, D}, [ww, L, D, F](const float* s, cudaStream_t st) {
     for (int l = 0; l < L; ++l) {
       cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * F * D, ww.w2 + (size_t)l * D * F, F, D, F, 1.0f);
@@ -434,18 +464,32 @@ struct SeqLayout {
 };
 
 // One Transformer stack (layers.py:989-1041) over the bf16 residual stream x [M, D] (in place).
-int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayout& sl, int act, cudaStream_t st) {
+// Fused-LN form (default): on entry stats_a holds (sum, sum of squares) of every row of x; each block is
+//   QKV GEMM on raw x with LN1 folded in -> attention -> out-proj + residual (emits stats of the new x into stats_b)
+//   -> FFN1 on raw x with LN2 folded in (+act) -> FFN2 + residual (emits stats into stats_a);
+// on exit stats_a again describes x.  With fuse_ln off, the two LayerNorms run as standalone kernels.
+int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayout& sl, int act, cudaStream_t st, float* stats_a,
+              int slots_a, float* stats_b) {
   const int D = w.D, F = w.F, H = w.H;
   bf16* n = static_cast<bf16*>(h->ws_n.p);
   bf16* qkv = static_cast<bf16*>(h->ws_qkv.p);
   bf16* u = static_cast<bf16*>(h->ws_u.p);
+  const bool fuse = h->fuse_ln && stats_a != nullptr;
+  const int gslots = vp::gemm_stats_slots(D);   // slots the residual GEMMs (N = D) write
   for (int l = 0; l < w.L; ++l) {
     vp::LnArgs ln;
-    ln.x = x; ln.ldx = D; ln.gamma1 = w.ln1_g + (size_t)l * D; ln.beta = w.ln1_b + (size_t)l * D; ln.y_bf16 = n; ln.M = M; ln.D = D;
-    CK(vp::launch_layernorm(st, ln)); h->launches++;
+    ln.x = x; ln.ldx = D; ln.y_bf16 = n; ln.M = M; ln.D = D;
     vp::GemmEpilogue e1;
-    e1.bias = w.bqkv + (size_t)l * 3 * D;
-    CK(vp::launch_gemm(st, n, D, w.wqkv + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->launches++;
+    if (fuse) {
+      e1.bias = w.c2_qkv + (size_t)l * 3 * D; e1.ln_stats_in = stats_a; e1.ln_slots = (l == 0) ? slots_a : gslots;
+      e1.ln_colsum = w.c1_qkv + (size_t)l * 3 * D; e1.ln_dim = D;
+      CK(vp::launch_gemm(st, x, D, w.wqkv_ln + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->launches++;
+    } else {
+      ln.gamma1 = w.ln1_g + (size_t)l * D; ln.beta = w.ln1_b + (size_t)l * D;
+      CK(vp::launch_layernorm(st, ln)); h->launches++;
+      e1.bias = w.bqkv + (size_t)l * 3 * D;
+      CK(vp::launch_gemm(st, n, D, w.wqkv + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->launches++;
+    }
     vp::AttnArgs at;
     at.q = qkv; at.k = qkv + D; at.v = qkv + 2 * D; at.ld = 3 * D; at.out = n; at.ldo = D;
     at.num_seq = sl.num_seq; at.S = sl.S; at.group = sl.group; at.heads = H; at.dh = D / H;
@@ -453,14 +497,23 @@ int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayo
     CK(vp::launch_attention(st, at)); h->launches++;
     vp::GemmEpilogue e2;
     e2.bias = w.bo + (size_t)l * D; e2.resid = x; e2.ldr = D;
+    if (fuse) e2.stats_out = stats_b;
     CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, x, D, M, D, D, e2)); h->launches++;
-    ln.gamma1 = w.ln2_g + (size_t)l * D; ln.beta = w.ln2_b + (size_t)l * D;
-    CK(vp::launch_layernorm(st, ln)); h->launches++;
     vp::GemmEpilogue e3;
-    e3.bias = w.b1 + (size_t)l * F; e3.act = act; e3.row_scale = sl.row_scale;
-    CK(vp::launch_gemm(st, n, D, w.w1 + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->launches++;
+    e3.act = act; e3.row_scale = sl.row_scale;
+    if (fuse) {
+      e3.bias = w.c2_ffn1 + (size_t)l * F; e3.ln_stats_in = stats_b; e3.ln_slots = gslots;
+      e3.ln_colsum = w.c1_ffn1 + (size_t)l * F; e3.ln_dim = D;
+      CK(vp::launch_gemm(st, x, D, w.w1_ln + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->launches++;
+    } else {
+      ln.gamma1 = w.ln2_g + (size_t)l * D; ln.beta = w.ln2_b + (size_t)l * D;
+      CK(vp::launch_layernorm(st, ln)); h->launches++;
+      e3.bias = w.b1 + (size_t)l * F;
+      CK(vp::launch_gemm(st, n, D, w.w1 + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->launches++;
+    }
     vp::GemmEpilogue e4;
     e4.bias = w.b2 + (size_t)l * D; e4.row_scale = sl.row_scale; e4.resid = x; e4.ldr = D;
+    if (fuse) e4.stats_out = stats_a;
     CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, x, D, M, D, F, e4)); h->launches++;
   }
   return VP_OK;
@@ -471,6 +524,7 @@ int ensure_workspace(vp_handle* h, size_t M, int D, int F) {
   CK(h->ws_n.ensure(M * D * sizeof(bf16)));
   CK(h->ws_qkv.ensure(M * 3 * D * sizeof(bf16)));
   CK(h->ws_u.ensure(M * F * sizeof(bf16)));
+  CK(h->ws_stats.ensure(2 * (M * 2 * 16 + 64) * sizeof(float)));   // two buffers of [M][<=16 slots][2]
   return VP_OK;
 }
 
@@ -515,28 +569,33 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
   if (in_dtype == VP_U8) CK(vp::launch_patchify_u8(st, static_cast<const uint8_t*>(video), patches, h->k_patch_pad, B * T, H, W, P));
   else CK(vp::launch_patchify(st, static_cast<const float*>(video), patches, h->k_patch_pad, B * T, H, W, P));
   h->launches++;
+  float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
+  float* stats_b = h->fuse_ln ? stats_a + (M * 2 * 16 + 64) : nullptr;
   vp::GemmEpilogue ep;
   ep.bias = h->b_patch; ep.pos_table = h->d_spatial_pos; ep.pos_period = N;
+  ep.stats_out = stats_a;
   CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->launches++;
 
   // spatial stack: sequences = frames (N contiguous tokens)
   SeqLayout sp{B * T, N, 1, 0, pad_tok, keep_tok};
-  if ((rc = run_stack(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st)) != VP_OK) return rc;
+  if ((rc = run_stack(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st, stats_a, vp::gemm_stats_slots(D), stats_b)) != VP_OK) return rc;
 
   // spatial_ln (+ temporal pos-emb add, encoders.py:528-553); in place on the residual stream
   vp::LnArgs ln;
   ln.x = x; ln.ldx = D; ln.gamma1 = h->sp_ln_g; ln.beta = h->sp_ln_b; ln.y_bf16 = x; ln.y_f32 = spatial_f32;
   ln.add_table = h->d_temporal_pos; ln.add_div = N; ln.add_mod = T; ln.M = (int)M; ln.D = D;
+  ln.stats_out = stats_a;   // statistics of LN(x) + Et: the input rows of temporal block 0
   CK(vp::launch_layernorm(st, ln)); h->launches++;
 
   // temporal stack: sequences = tubes (T tokens, N rows apart)
   SeqLayout tp{B * N, T, N, 0, pad_tube, keep_tok};
-  if ((rc = run_stack(h, h->temporal, x, (int)M, tp, vp::ACT_GELU, st)) != VP_OK) return rc;
+  if ((rc = run_stack(h, h->temporal, x, (int)M, tp, vp::ACT_GELU, st, stats_a, 1, stats_b)) != VP_OK) return rc;
 
   // temporal_ln (:567-569); '(bn)td->b(tn)d' (:570-572) is the identity in this layout
   vp::LnArgs lo;
   lo.x = x; lo.ldx = D; lo.gamma1 = h->tp_ln_g; lo.beta = h->tp_ln_b; lo.y_bf16 = final_ln_in_place ? x : out_bf16; lo.y_f32 = out_f32;
   lo.M = (int)M; lo.D = D;
+  if (final_ln_in_place) lo.stats_out = stats_a;   // the auxiliary encoder continues on LN(x)
   CK(vp::launch_layernorm(st, lo)); h->launches++;
   if (M_out) *M_out = M;
   return VP_OK;
@@ -566,6 +625,7 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
   vp_handle* h = new vp_handle();
   h->cfg = *cfg;
   if (const char* ev = getenv("VP_HOST_CHUNK_CLIPS")) h->host_chunk_clips = atoi(ev);   // tuning knob of the host pipeline
+  if (const char* ev = getenv("VP_FUSE_LN")) h->fuse_ln = atoi(ev) != 0;
   cudaGetDevice(&h->device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, h->device);
@@ -589,6 +649,7 @@ void vp_destroy(vp_handle* h) {
   if (h == nullptr) return;
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
+
   if (h->d_spatial_pos) cudaFree(h->d_spatial_pos);
   if (h->d_temporal_pos) cudaFree(h->d_temporal_pos);
   if (h->d_pe) cudaFree(h->d_pe);
@@ -597,7 +658,7 @@ void vp_destroy(vp_handle* h) {
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_comp[i]); cudaEventDestroy(h->ev_out[i]); }
     cudaEventDestroy(h->ev_start);
   }
-  DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool};
+  DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats};
   for (DevBuf* b : bufs) b->release();
   delete h;
 }
@@ -632,11 +693,32 @@ int vp_set_weight(vp_handle* h, const char* key, const void* data, const int64_t
   return VP_OK;
 }
 
+static int finalize_stack(vp_handle* h, StackWeights* w) {
+  const int L = w->L, D = w->D, F = w->F;
+  const float qscale = 1.0f / sqrtf(static_cast<float>(D / w->H));
+  for (int l = 0; l < L; ++l) {
+    for (int i = 0; i < 3; ++i) {
+      CK(vp::launch_fold_ln_weight(0, w->f_wqkv + ((size_t)l * 3 + i) * D * D, w->ln1_g + (size_t)l * D, w->ln1_b + (size_t)l * D,
+                                   w->f_bqkv + ((size_t)l * 3 + i) * D, w->wqkv_ln + (size_t)l * 3 * D * D + (size_t)i * D * D,
+                                   w->c1_qkv + (size_t)l * 3 * D + (size_t)i * D, w->c2_qkv + (size_t)l * 3 * D + (size_t)i * D, D, D, D,
+                                   i == 0 ? qscale : 1.0f));
+    }
+    CK(vp::launch_fold_ln_weight(0, w->f_w1 + (size_t)l * D * F, w->ln2_g + (size_t)l * D, w->ln2_b + (size_t)l * D, w->f_b1 + (size_t)l * F,
+                                 w->w1_ln + (size_t)l * F * D, w->c1_ffn1 + (size_t)l * F, w->c2_ffn1 + (size_t)l * F, D, F, D, 1.0f));
+  }
+  CK(cudaStreamSynchronize(0));
+  return VP_OK;
+}
+
 int vp_finalize(vp_handle* h) {
   if (h == nullptr) return VP_ERR_INVALID;
   cudaSetDevice(h->device);
   for (const ParamSpec& s : h->specs)
     if (!s.set) return h->fail(VP_ERR_INCOMPLETE, "parameter '%s' was never set", s.key.c_str());
+  for (StackWeights* w : h->stacks) {
+    int rc = finalize_stack(h, w);
+    if (rc != VP_OK) return rc;
+  }
   if (h->cfg.kind == VP_KIND_CLIP) {
     int rc = finalize_pooler(h);
     if (rc != VP_OK) return rc;
@@ -767,7 +849,9 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   const int N = (int)(M / ((size_t)B * T));
   if (c.num_auxiliary_layers > 0) {  // auxiliary_encoder: full attention over all T*N tokens of a clip (:846-857)
     SeqLayout ax{B, T * N, 1, 0, nullptr, nullptr};
-    if ((rc = run_stack(h, h->aux, x, (int)M, ax, vp::ACT_GELU, st)) != VP_OK) return rc;
+    float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
+    float* stats_b = h->fuse_ln ? stats_a + (M * 2 * 16 + 64) : nullptr;
+    if ((rc = run_stack(h, h->aux, x, (int)M, ax, vp::ACT_GELU, st, stats_a, 1, stats_b)) != VP_OK) return rc;
   }
   const int ph = 4 * D / c.num_heads;
   size_t need = vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph);
@@ -803,7 +887,10 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->launches++;
   SeqLayout tl{Q, S, 1, 1, pad_ext, keep};
-  if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st)) != VP_OK) return rc;
+  float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
+  float* stats_b = h->fuse_ln ? stats_a + (M * 2 * 16 + 64) : nullptr;
+  if (stats_a) { CK(vp::launch_row_stats(st, x, D, stats_a, (int)M, D)); h->launches++; }
+  if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st, stats_a, 1, stats_b)) != VP_OK) return rc;
   // unimodal_ln on the class token only (features[:, -1], encoders.py:756-758,:906), then l2 normalise
   float* tmp = static_cast<float*>(h->ws_misc.p) + 2 * Mp;
   vp::LnArgs ln;
@@ -885,6 +972,28 @@ int vp_gemm_bf16(const void* A, int lda, const void* Wt, int ldb, void* C, int l
   e.pos_table = pos_table; e.pos_period = pos_period; e.out_f32 = out_f32;
   return ck(vp::launch_gemm(static_cast<cudaStream_t>(stream), static_cast<const bf16*>(A), lda, static_cast<const bf16*>(Wt), ldb, C,
                             ldc, M, N, K, e));
+}
+
+int vp_gemm_bf16_ln(const void* A, int lda, const void* Wt, int ldb, void* C, int ldc, int M, int N, int K, const float* bias, int act,
+                    const void* resid, int ldr, const float* ln_stats_in, int ln_slots, const float* ln_colsum, int ln_dim,
+                    float* stats_out, void* stream) {
+  vp::GemmEpilogue e;
+  e.bias = bias; e.act = act; e.resid = static_cast<const bf16*>(resid); e.ldr = ldr;
+  e.ln_stats_in = ln_stats_in; e.ln_slots = ln_slots; e.ln_colsum = ln_colsum; e.ln_dim = ln_dim; e.stats_out = stats_out;
+  return ck(vp::launch_gemm(static_cast<cudaStream_t>(stream), static_cast<const bf16*>(A), lda, static_cast<const bf16*>(Wt), ldb, C,
+                            ldc, M, N, K, e));
+}
+
+int vp_gemm_stats_slots(int N) { return vp::gemm_stats_slots(N); }
+
+int vp_row_stats(const void* x, int ldx, float* stats, int M, int D, void* stream) {
+  return ck(vp::launch_row_stats(static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx, stats, M, D));
+}
+
+int vp_fold_ln_weight(const float* src, const float* gamma1, const float* beta, const float* bias_in, void* dst, float* colsum,
+                      float* bias_out, int K, int N, int ldk, float scale, void* stream) {
+  return ck(vp::launch_fold_ln_weight(static_cast<cudaStream_t>(stream), src, gamma1, beta, bias_in, static_cast<bf16*>(dst), colsum,
+                                      bias_out, K, N, ldk, scale));
 }
 
 int vp_layernorm(const void* x, int ldx, const float* gamma1, const float* beta, void* y_bf16, float* y_f32,

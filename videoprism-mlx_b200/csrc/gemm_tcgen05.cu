@@ -62,6 +62,12 @@ struct KParams {
   int pos_period;
   const bf16* resid;
   int ldr;
+  const float* ln_stats_in;
+  int ln_slots;
+  const float* ln_colsum;
+  float ln_inv_dim;
+  float* stats_out;
+  int stats_slots;
 };
 
 __device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -239,6 +245,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const f32x2 rscale2 = pk2(rscale, rscale);
       const float* pos_row = nullptr;
       if (p.pos_table != nullptr) pos_row = p.pos_table + static_cast<size_t>(m % p.pos_period) * p.N;
+      // folded LayerNorm of the A rows: v = ln_a * acc + ln_b * colsum[n] + bias[n]
+      f32x2 ln_a2 = pk2(1.f, 1.f), ln_b2 = pk2(0.f, 0.f);
+      if (p.ln_stats_in != nullptr) {
+        float2 ss = make_float2(0.f, 0.f);
+        if (row_ok) {
+          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats_in) + static_cast<size_t>(m) * p.ln_slots;
+          for (int sl = 0; sl < p.ln_slots; ++sl) {   // fixed order: bit-reproducible statistics
+            const float2 t = __ldg(sp + sl);
+            ss.x += t.x; ss.y += t.y;
+          }
+        }
+        const float mean = ss.x * p.ln_inv_dim;
+        const float var = fmaxf(ss.y * p.ln_inv_dim - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-6f);
+        ln_a2 = pk2(rstd, rstd);
+        ln_b2 = pk2(-rstd * mean, -rstd * mean);
+      }
+      float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
         const int col = half * kColsPerWarp + ch * 32;
@@ -248,6 +272,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             bv[g] = (n0 + col + g * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 cs[8];
+        if (p.ln_stats_in != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            cs[g] = (n0 + col + g * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + col + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + col + (static_cast<uint32_t>(q * 32) << 16), r);
@@ -264,6 +294,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         f32x2 v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
+        if (p.ln_stats_in != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            v[2 * g] = fma2(v[2 * g], ln_a2, mul2(pk2(cs[g].x, cs[g].y), ln_b2));
+            v[2 * g + 1] = fma2(v[2 * g + 1], ln_a2, mul2(pk2(cs[g].z, cs[g].w), ln_b2));
+          }
+        }
         if (p.bias != nullptr) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -345,6 +382,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               upk2(v[4 * c + j], lo, hi);
               w[j] = pack_bf16x2(lo, hi);
             }
+            if (p.stats_out != nullptr && n + c * 8 < p.N) {
+              // statistics of the ROUNDED values: exactly what the next (LayerNorm-folded) GEMM will read
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+                st_sum += lo + hi;
+                st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+              }
+            }
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((c ^ sw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
           }
           fence_proxy_async_smem();
@@ -362,6 +408,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
+      }
+      if (!OUT_F32 && p.stats_out != nullptr && row_ok) {
+        const int slot = (tile % num_n_tiles) * 2 + half;
+        reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(m) * p.stats_slots + slot] = make_float2(st_sum, st_sq);
       }
     }
     if (!OUT_F32 && lane == 0) tma_store_wait<0>();
@@ -474,6 +524,11 @@ cudaError_t launch_gemm_bn(cudaStream_t s, const Maps& m, const KParams& kp, int
 
 }  // namespace
 
+int gemm_stats_slots(int N) {
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  return 2 * ((N + BN - 1) / BN);
+}
+
 cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, int ldb, void* Cout, int ldc, int M, int N,
                         int K, const GemmEpilogue& epi) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
@@ -507,6 +562,12 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   kp.pos_table = epi.pos_table;
   kp.pos_period = epi.pos_period > 0 ? epi.pos_period : 1;
   kp.resid = epi.resid; kp.ldr = epi.ldr;
+  kp.ln_stats_in = epi.ln_stats_in; kp.ln_colsum = epi.ln_colsum; kp.ln_slots = epi.ln_slots > 0 ? epi.ln_slots : 1;
+  kp.stats_slots = gemm_stats_slots(N);
+  kp.ln_inv_dim = epi.ln_dim > 0 ? 1.0f / static_cast<float>(epi.ln_dim) : 0.f;
+  kp.stats_out = epi.stats_out;
+  if (epi.ln_stats_in != nullptr && (epi.ln_colsum == nullptr || epi.ln_dim <= 0)) return cudaErrorInvalidValue;
+  if (epi.stats_out != nullptr && epi.out_f32) return cudaErrorInvalidValue;
   if (CG == 2) {
     const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
     return launch_gemm_bn<256, 2>(s, m, kp, 2 * pairs, epi.act, epi.resid != nullptr, epi.out_f32 != 0);

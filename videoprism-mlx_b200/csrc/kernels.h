@@ -22,7 +22,20 @@ struct GemmEpilogue {
   const bf16* resid = nullptr;       // [M, ldr] bf16 residual stream (layers.py:855, :425); may alias C
   int ldr = 0;
   int out_f32 = 0;                   // C is float* when set
+  // LayerNorm folded into the GEMM (layers.py:237-270 applied to the A rows):  A holds the RAW rows x, Wt holds
+  // (gamma1 (.) W)^T, and   v = rstd[m] * acc - rstd[m] * mean[m] * ln_colsum[n] + bias[n]   with bias = beta.W + b.
+  // ln_stats_in [M][ln_slots][2] = partial (sum, sum of squares) of each A row over its ln_dim features; the
+  // partials are added in slot order (deterministic).
+  const float* ln_stats_in = nullptr;
+  int ln_slots = 1;
+  const float* ln_colsum = nullptr;  // [N] column sums of the bf16-rounded (gamma1 (.) W)
+  int ln_dim = 0;
+  // Emit partial (sum, sum of squares) of every stored bf16 output row into stats_out [M][gemm_stats_slots(N)][2]:
+  // one slot per (column tile, epilogue half), each written exactly once (no atomics, no zeroing).  The statistics
+  // the NEXT LayerNorm-folded GEMM needs.  Requires N == the full feature dimension.
+  float* stats_out = nullptr;
 };
+int gemm_stats_slots(int N);   // slots per row a GEMM with N output columns writes into stats_out
 
 // C[M,N] = A[M,K] (bf16, row-major, lda) * Wt[N,K]^T (bf16, row-major, ldb) with epilogue.
 // Requirements: K % 8 == 0, N % 8 == 0, lda % 8 == 0, ldb % 8 == 0, 16-byte aligned bases.
@@ -37,6 +50,7 @@ struct LnArgs {
   const float* beta = nullptr;    // [D]
   bf16* y_bf16 = nullptr;         // [M, D] or null
   float* y_f32 = nullptr;         // [M, D] or null (LN(x) without the table add)
+  float* stats_out = nullptr;     // [M][1][2] (sum, sum of squares) of the stored bf16 rows y_bf16 (one slot), or null
   const float* add_table = nullptr; int add_div = 1; int add_mod = 1;   // temporal pos-emb, encoders.py:553
   int M = 0, D = 0;
 };
@@ -73,6 +87,14 @@ cudaError_t launch_transpose_cast(cudaStream_t s, const float* src, bf16* dst, i
 cudaError_t launch_cast_bf16(cudaStream_t s, const float* src, bf16* dst, size_t n, float scale);
 // dst fp32 = a * src + b
 cudaError_t launch_affine_f32(cudaStream_t s, const float* src, float* dst, size_t n, float a, float b);
+
+// (sum, sum of squares) of each bf16 row: stats [M][2]
+cudaError_t launch_row_stats(cudaStream_t s, const bf16* x, int ldx, float* stats, int M, int D);
+// LayerNorm folding of a projection weight (load time):  src fp32 [K, N] (Flax [in, out]) ->
+//   dst bf16 [N, ldk] = (gamma1[k] * src[k, n] * scale)^T ;  colsum[n] = sum_k float(dst[n, k]) ;
+//   bias_out[n] = sum_k beta[k] * src[k, n] * scale + bias_in[n] * scale
+cudaError_t launch_fold_ln_weight(cudaStream_t s, const float* src, const float* gamma1, const float* beta, const float* bias_in,
+                                  bf16* dst, float* colsum, float* bias_out, int K, int N, int ldk, float scale);
 
 // L2 normalise rows in fp32 (encoders.py:50-67): y = x / sqrt(sum(x^2) + 1e-12)
 cudaError_t launch_l2norm(cudaStream_t s, const float* x, float* y, int rows, int D);
