@@ -125,6 +125,11 @@ VP_API int vp_similarity(const float* v, const float* t, float* sim, int Nv, int
 VP_API size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W); /* device bytes a forward of this shape needs */
 VP_API int64_t vp_kernel_launches(const vp_handle* h);  /* kernels launched by this handle so far */
 VP_API int vp_device_sm_count(void);                    /* < 0 when no CUDA device is usable */
+/* In-situ timeline (diagnostic; the reference's counterpart is scripts/benchmark_performance.py's per-stage timers):
+ * vp_trace(h, 1) starts recording one CUDA event after every kernel this handle launches (on the launch stream),
+ * vp_trace_report synchronises and writes "label count total_ms" lines (+ "TOTAL n ms") into buf, vp_trace(h, 0) stops. */
+VP_API int vp_trace(vp_handle* h, int enable);
+VP_API int vp_trace_report(vp_handle* h, char* buf, int cap);
 
 /* -- kernel-level entry points (device pointers; used by the parity tests and micro-benchmarks) ---
  *    C[M,N] = A[M,K] * Wt[N,K]^T (+bias[N]) ; act 0 none, 1 exact GELU, 2 ReLU ; optional bf16 residual. */

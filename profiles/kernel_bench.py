@@ -20,10 +20,37 @@ M = B * T * N
 st = int(torch.cuda.current_stream().cuda_stream)
 
 
+SUSTAINED = float(os.environ.get("VP_KB_SUSTAINED_S", "0"))   # > 0: run every kernel back to back for this many seconds
+                                                                # (power-capped steady state) and sample clocks / power
+
+
+def _smi():
+    import subprocess
+    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-i", "0"],
+                         capture_output=True, text=True).stdout.strip().split(",")
+    return float(out[0]), float(out[1])
+
+
 def timeit(fn, reps=20):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if SUSTAINED > 0:
+        import time
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        n = max(20, int(SUSTAINED * 1e3 / max(e0.elapsed_time(e1), 1e-3)))
+        for _ in range(n // 2):   # reach the steady state first
+            fn()
+        e0.record()
+        for _ in range(n // 2):
+            fn()
+        e1.record()
+        time.sleep(SUSTAINED * 0.25)
+        mhz, watts = _smi()      # sampled while the second half is still running
+        torch.cuda.synchronize()
+        print(f"      [sustained {n // 2} launches: {mhz:.0f} MHz, {watts:.0f} W]", end=" ")
+        return e0.elapsed_time(e1) / (n // 2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -41,6 +68,27 @@ def gemm(Mm, Nn, Kk, act=0, resid=False):
     def f():
         rc = lib.vp_gemm_bf16(A.data_ptr(), Kk, Wt.data_ptr(), Kk, C.data_ptr(), Nn, Mm, Nn, Kk, bias.data_ptr(), act,
                               C.data_ptr() if resid else None, Nn if resid else 0, None, None, 0, 0, st)
+        assert rc == 0
+    ms = timeit(f)
+    return ms, 2.0 * Mm * Nn * Kk / ms / 1e9
+
+
+def gemm_ln(Mm, Nn, Kk, act=0, resid=False, stats_out=False):
+    """The engine's LayerNorm-folded form: raw A rows + per-row (sum, sumsq) slots + column sums (vp_gemm_bf16_ln)."""
+    A = (torch.randn((Mm, Kk), device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn((Nn, Kk), device="cuda") * 0.02).bfloat16()
+    bias = torch.zeros((Nn,), device="cuda")
+    colsum = Wt.float().sum(1).contiguous()
+    slots = lib.vp_gemm_stats_slots(Kk)
+    stats = torch.zeros((Mm, slots, 2), device="cuda")
+    stats[:, 0, 0] = A.float().sum(1)
+    stats[:, 0, 1] = (A.float() ** 2).sum(1)
+    C = torch.zeros((Mm, Nn), dtype=torch.bfloat16, device="cuda")
+    so = torch.zeros((Mm, lib.vp_gemm_stats_slots(Nn), 2), device="cuda") if stats_out else None
+    def f():
+        rc = lib.vp_gemm_bf16_ln(A.data_ptr(), Kk, Wt.data_ptr(), Kk, C.data_ptr(), Nn, Mm, Nn, Kk, bias.data_ptr(), act,
+                                 C.data_ptr() if resid else None, Nn if resid else 0, stats.data_ptr(), slots, colsum.data_ptr(), Kk,
+                                 so.data_ptr() if stats_out else None, st)
         assert rc == 0
     ms = timeit(f)
     return ms, 2.0 * Mm * Nn * Kk / ms / 1e9
@@ -73,6 +121,14 @@ print(f"B={B} model={model} M={M}")
 for name, args in [("QKV   ", (M, 3 * D, D, 0, False)), ("outprj", (M, D, D, 0, True)), ("FFN1  ", (M, F, D, 1, False)), ("FFN2  ", (M, D, F, 0, True))]:
     ms, tf = gemm(*args)
     print(f"gemm {name} {args[0]}x{args[1]}x{args[2]}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = gemm_ln(M, 3 * D, D)
+print(f"gemm QKV    LN-folded            : {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = gemm_ln(M, F, D, act=1)
+print(f"gemm FFN1   LN-folded + GELU     : {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = gemm_ln(M, D, F, resid=True, stats_out=True)
+print(f"gemm FFN2   resid + stats_out    : {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+ms, tf = gemm_ln(M, D, D, resid=True, stats_out=True)
+print(f"gemm outprj resid + stats_out    : {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
 ms, tf = attention(B * T, N, 1)
 print(f"attention spatial (tcgen05): {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
 ms, tf = attention(B * T, N, 1, qscale=1.0)

@@ -46,6 +46,8 @@ _PROTOS = {
     "vp_workspace_bytes": (C.c_size_t, [_P, _I, _I, _I, _I]),
     "vp_kernel_launches": (C.c_int64, [_P]),
     "vp_device_sm_count": (_I, []),
+    "vp_trace": (_I, [_P, _I]),
+    "vp_trace_report": (_I, [_P, C.c_char_p, _I]),
     "vp_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
     "vp_gemm_bf16_ln": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P]),
     "vp_gemm_stats_slots": (_I, [_I]),

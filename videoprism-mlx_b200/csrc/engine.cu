@@ -85,6 +85,17 @@ struct vp_handle {
   bool finalized = false;
   int64_t launches = 0;
   DevBuf staging;
+  // in-situ timeline (vp_trace): one CUDA event after every launch, labelled; off by default
+  bool trace_on = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> trace;
+  void mark(cudaStream_t st, const char* label, bool counts = true) {
+    if (counts) launches++;
+    if (!trace_on) return;
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    trace.emplace_back(label, ev);
+  }
 
   // encoder
   bf16* w_patch = nullptr; float* b_patch = nullptr; int k_patch = 0, k_patch_pad = 0;
@@ -110,6 +121,7 @@ struct vp_handle {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
   int host_chunk_clips = 0;   // 0 = automatic
+  size_t stats_stride = 0;    // floats between the two LayerNorm-statistics buffers
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -457,6 +469,12 @@ int prepare_pe(vp_handle* h, int L, cudaStream_t st) {
   return VP_OK;
 }
 
+// trace labels of one stack: layernorm, qkv, attention, out-proj, ffn1, ffn2
+const char* const kTagSpatial[6] = {"spatial.ln", "spatial.qkv", "spatial.attn", "spatial.outproj", "spatial.ffn1", "spatial.ffn2"};
+const char* const kTagTemporal[6] = {"temporal.ln", "temporal.qkv", "temporal.attn", "temporal.outproj", "temporal.ffn1", "temporal.ffn2"};
+const char* const kTagAux[6] = {"aux.ln", "aux.qkv", "aux.attn", "aux.outproj", "aux.ffn1", "aux.ffn2"};
+const char* const kTagText[6] = {"text.ln", "text.qkv", "text.attn", "text.outproj", "text.ffn1", "text.ffn2"};
+
 struct SeqLayout {
   int num_seq, S, group, causal;
   const float* key_pad;    // [num_seq, S] or null
@@ -469,7 +487,7 @@ struct SeqLayout {
 //   -> FFN1 on raw x with LN2 folded in (+act) -> FFN2 + residual (emits stats into stats_a);
 // on exit stats_a again describes x.  With fuse_ln off, the two LayerNorms run as standalone kernels.
 int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayout& sl, int act, cudaStream_t st, float* stats_a,
-              int slots_a, float* stats_b) {
+              int slots_a, float* stats_b, const char* const* tag) {
   const int D = w.D, F = w.F, H = w.H;
   bf16* n = static_cast<bf16*>(h->ws_n.p);
   bf16* qkv = static_cast<bf16*>(h->ws_qkv.p);
@@ -483,38 +501,38 @@ int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayo
     if (fuse) {
       e1.bias = w.c2_qkv + (size_t)l * 3 * D; e1.ln_stats_in = stats_a; e1.ln_slots = (l == 0) ? slots_a : gslots;
       e1.ln_colsum = w.c1_qkv + (size_t)l * 3 * D; e1.ln_dim = D;
-      CK(vp::launch_gemm(st, x, D, w.wqkv_ln + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->launches++;
+      CK(vp::launch_gemm(st, x, D, w.wqkv_ln + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->mark(st, tag[1]);
     } else {
       ln.gamma1 = w.ln1_g + (size_t)l * D; ln.beta = w.ln1_b + (size_t)l * D;
-      CK(vp::launch_layernorm(st, ln)); h->launches++;
+      CK(vp::launch_layernorm(st, ln)); h->mark(st, tag[0]);
       e1.bias = w.bqkv + (size_t)l * 3 * D;
-      CK(vp::launch_gemm(st, n, D, w.wqkv + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->launches++;
+      CK(vp::launch_gemm(st, n, D, w.wqkv + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->mark(st, tag[1]);
     }
     vp::AttnArgs at;
     at.q = qkv; at.k = qkv + D; at.v = qkv + 2 * D; at.ld = 3 * D; at.out = n; at.ldo = D;
     at.num_seq = sl.num_seq; at.S = sl.S; at.group = sl.group; at.heads = H; at.dh = D / H;
     at.cap = h->cfg.atten_logit_cap; at.key_pad = sl.key_pad; at.causal = sl.causal;
-    CK(vp::launch_attention(st, at)); h->launches++;
+    CK(vp::launch_attention(st, at)); h->mark(st, tag[2]);
     vp::GemmEpilogue e2;
     e2.bias = w.bo + (size_t)l * D; e2.resid = x; e2.ldr = D;
     if (fuse) e2.stats_out = stats_b;
-    CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, x, D, M, D, D, e2)); h->launches++;
+    CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, x, D, M, D, D, e2)); h->mark(st, tag[3]);
     vp::GemmEpilogue e3;
     e3.act = act; e3.row_scale = sl.row_scale;
     if (fuse) {
       e3.bias = w.c2_ffn1 + (size_t)l * F; e3.ln_stats_in = stats_b; e3.ln_slots = gslots;
       e3.ln_colsum = w.c1_ffn1 + (size_t)l * F; e3.ln_dim = D;
-      CK(vp::launch_gemm(st, x, D, w.w1_ln + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->launches++;
+      CK(vp::launch_gemm(st, x, D, w.w1_ln + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->mark(st, tag[4]);
     } else {
       ln.gamma1 = w.ln2_g + (size_t)l * D; ln.beta = w.ln2_b + (size_t)l * D;
-      CK(vp::launch_layernorm(st, ln)); h->launches++;
+      CK(vp::launch_layernorm(st, ln)); h->mark(st, tag[0]);
       e3.bias = w.b1 + (size_t)l * F;
-      CK(vp::launch_gemm(st, n, D, w.w1 + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->launches++;
+      CK(vp::launch_gemm(st, n, D, w.w1 + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->mark(st, tag[4]);
     }
     vp::GemmEpilogue e4;
     e4.bias = w.b2 + (size_t)l * D; e4.row_scale = sl.row_scale; e4.resid = x; e4.ldr = D;
     if (fuse) e4.stats_out = stats_a;
-    CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, x, D, M, D, F, e4)); h->launches++;
+    CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, x, D, M, D, F, e4)); h->mark(st, tag[5]);
   }
   return VP_OK;
 }
@@ -524,7 +542,9 @@ int ensure_workspace(vp_handle* h, size_t M, int D, int F) {
   CK(h->ws_n.ensure(M * D * sizeof(bf16)));
   CK(h->ws_qkv.ensure(M * 3 * D * sizeof(bf16)));
   CK(h->ws_u.ensure(M * F * sizeof(bf16)));
-  CK(h->ws_stats.ensure(2 * (M * 2 * 16 + 64) * sizeof(float)));   // two buffers of [M][<=16 slots][2]
+  const int sl = vp::gemm_stats_slots(D) > 16 ? vp::gemm_stats_slots(D) : 16;
+  h->stats_stride = M * 2 * (size_t)sl + 64;
+  CK(h->ws_stats.ensure(2 * h->stats_stride * sizeof(float)));   // two buffers of [M][slots][2]
   return VP_OK;
 }
 
@@ -561,42 +581,43 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
   if (frame_pad != nullptr) {
     CK(h->ws_misc.ensure(3 * M * sizeof(float)));
     float* base = static_cast<float*>(h->ws_misc.p);
-    CK(vp::launch_pad_expand(st, frame_pad, base, base + M, base + 2 * M, B, T, N)); h->launches++;
+    CK(vp::launch_pad_expand(st, frame_pad, base, base + M, base + 2 * M, B, T, N)); h->mark(st, "pad_expand");
     pad_tok = base; keep_tok = base + M; pad_tube = base + 2 * M;
   }
 
+  h->mark(st, nullptr, false);   // trace: start of this forward
   // patchify + cast (encoders.py:436-439), patch projection + spatial pos-emb (:488-514)
   if (in_dtype == VP_U8) CK(vp::launch_patchify_u8(st, static_cast<const uint8_t*>(video), patches, h->k_patch_pad, B * T, H, W, P));
   else CK(vp::launch_patchify(st, static_cast<const float*>(video), patches, h->k_patch_pad, B * T, H, W, P));
-  h->launches++;
+  h->mark(st, "patchify");
   float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
-  float* stats_b = h->fuse_ln ? stats_a + (M * 2 * 16 + 64) : nullptr;
+  float* stats_b = h->fuse_ln ? stats_a + h->stats_stride : nullptr;
   vp::GemmEpilogue ep;
   ep.bias = h->b_patch; ep.pos_table = h->d_spatial_pos; ep.pos_period = N;
   ep.stats_out = stats_a;
-  CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->launches++;
+  CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->mark(st, "patch_proj");
 
   // spatial stack: sequences = frames (N contiguous tokens)
   SeqLayout sp{B * T, N, 1, 0, pad_tok, keep_tok};
-  if ((rc = run_stack(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st, stats_a, vp::gemm_stats_slots(D), stats_b)) != VP_OK) return rc;
+  if ((rc = run_stack(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st, stats_a, vp::gemm_stats_slots(D), stats_b, kTagSpatial)) != VP_OK) return rc;
 
   // spatial_ln (+ temporal pos-emb add, encoders.py:528-553); in place on the residual stream
   vp::LnArgs ln;
   ln.x = x; ln.ldx = D; ln.gamma1 = h->sp_ln_g; ln.beta = h->sp_ln_b; ln.y_bf16 = x; ln.y_f32 = spatial_f32;
   ln.add_table = h->d_temporal_pos; ln.add_div = N; ln.add_mod = T; ln.M = (int)M; ln.D = D;
   ln.stats_out = stats_a;   // statistics of LN(x) + Et: the input rows of temporal block 0
-  CK(vp::launch_layernorm(st, ln)); h->launches++;
+  CK(vp::launch_layernorm(st, ln)); h->mark(st, "spatial_ln");
 
   // temporal stack: sequences = tubes (T tokens, N rows apart)
   SeqLayout tp{B * N, T, N, 0, pad_tube, keep_tok};
-  if ((rc = run_stack(h, h->temporal, x, (int)M, tp, vp::ACT_GELU, st, stats_a, 1, stats_b)) != VP_OK) return rc;
+  if ((rc = run_stack(h, h->temporal, x, (int)M, tp, vp::ACT_GELU, st, stats_a, 1, stats_b, kTagTemporal)) != VP_OK) return rc;
 
   // temporal_ln (:567-569); '(bn)td->b(tn)d' (:570-572) is the identity in this layout
   vp::LnArgs lo;
   lo.x = x; lo.ldx = D; lo.gamma1 = h->tp_ln_g; lo.beta = h->tp_ln_b; lo.y_bf16 = final_ln_in_place ? x : out_bf16; lo.y_f32 = out_f32;
   lo.M = (int)M; lo.D = D;
   if (final_ln_in_place) lo.stats_out = stats_a;   // the auxiliary encoder continues on LN(x)
-  CK(vp::launch_layernorm(st, lo)); h->launches++;
+  CK(vp::launch_layernorm(st, lo)); h->mark(st, "temporal_ln");
   if (M_out) *M_out = M;
   return VP_OK;
 }
@@ -850,8 +871,8 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   if (c.num_auxiliary_layers > 0) {  // auxiliary_encoder: full attention over all T*N tokens of a clip (:846-857)
     SeqLayout ax{B, T * N, 1, 0, nullptr, nullptr};
     float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
-    float* stats_b = h->fuse_ln ? stats_a + (M * 2 * 16 + 64) : nullptr;
-    if ((rc = run_stack(h, h->aux, x, (int)M, ax, vp::ACT_GELU, st, stats_a, 1, stats_b)) != VP_OK) return rc;
+    float* stats_b = h->fuse_ln ? stats_a + h->stats_stride : nullptr;
+    if ((rc = run_stack(h, h->aux, x, (int)M, ax, vp::ACT_GELU, st, stats_a, 1, stats_b, kTagAux)) != VP_OK) return rc;
   }
   const int ph = 4 * D / c.num_heads;
   size_t need = vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph);
@@ -888,9 +909,9 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
   CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->launches++;
   SeqLayout tl{Q, S, 1, 1, pad_ext, keep};
   float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
-  float* stats_b = h->fuse_ln ? stats_a + (M * 2 * 16 + 64) : nullptr;
+  float* stats_b = h->fuse_ln ? stats_a + h->stats_stride : nullptr;
   if (stats_a) { CK(vp::launch_row_stats(st, x, D, stats_a, (int)M, D)); h->launches++; }
-  if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st, stats_a, 1, stats_b)) != VP_OK) return rc;
+  if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st, stats_a, 1, stats_b, kTagText)) != VP_OK) return rc;
   // unimodal_ln on the class token only (features[:, -1], encoders.py:756-758,:906), then l2 normalise
   float* tmp = static_cast<float*>(h->ws_misc.p) + 2 * Mp;
   vp::LnArgs ln;
@@ -954,6 +975,46 @@ size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W) {
 }
 
 int64_t vp_kernel_launches(const vp_handle* h) { return h ? h->launches : 0; }
+
+// In-situ timeline: with tracing on, every launch is followed by a CUDA event on the launch stream; the report
+// aggregates the event-to-event times by label ("label count total_ms" per line, then "TOTAL n ms").
+int vp_trace(vp_handle* h, int enable) {
+  if (h == nullptr) return VP_ERR_INVALID;
+  for (auto& t : h->trace) cudaEventDestroy(t.second);
+  h->trace.clear();
+  h->trace_on = enable != 0;
+  return VP_OK;
+}
+
+int vp_trace_report(vp_handle* h, char* buf, int cap) {
+  if (h == nullptr || buf == nullptr || cap <= 0) return VP_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaDeviceSynchronize());
+  std::vector<std::string> order;
+  std::map<std::string, std::pair<int, double>> agg;
+  double total = 0.0;
+  int n = 0;
+  for (size_t i = 1; i < h->trace.size(); ++i) {
+    if (h->trace[i].first == nullptr) continue;   // start marker of the next forward: the gap before it is not a kernel
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->trace[i - 1].second, h->trace[i].second) != cudaSuccess) continue;
+    auto it = agg.find(h->trace[i].first);
+    if (it == agg.end()) { order.push_back(h->trace[i].first); it = agg.emplace(h->trace[i].first, std::make_pair(0, 0.0)).first; }
+    it->second.first++; it->second.second += ms;
+    total += ms; n++;
+  }
+  std::string out;
+  char line[160];
+  for (const std::string& k : order) {
+    snprintf(line, sizeof(line), "%s %d %.6f\n", k.c_str(), agg[k].first, agg[k].second);
+    out += line;
+  }
+  snprintf(line, sizeof(line), "TOTAL %d %.6f\n", n, total);
+  out += line;
+  if ((int)out.size() + 1 > cap) return h->fail(VP_ERR_INVALID, "trace report needs %d bytes", (int)out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return VP_OK;
+}
 
 int vp_device_sm_count(void) {
   int n = 0;

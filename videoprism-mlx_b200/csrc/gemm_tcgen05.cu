@@ -4,17 +4,18 @@
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles)
 //   warp 1      : MMA issuer    (one elected thread, tcgen05.mma kind::f16, M=128 x N=BN x K=16)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue      (tcgen05.ld -> bias / GELU / row-scale / pos-emb / residual -> bf16)
+//   warps 4..19 : epilogue      (tcgen05.ld -> folded LayerNorm / bias / GELU / row-scale / pos-emb / residual -> bf16)
 // The fp32 accumulator lives in TMEM and is double buffered (2 x BN columns), so the epilogue of
 // tile i overlaps the main loop of tile i+1.  The smem ring has kStages slots of (128 x 64 A,
 // BN x 64 B) bf16.
 //
-// Epilogue data movement is all TMA: each epilogue warp owns 32 accumulator rows and walks its
-// columns in 32-column chunks; a chunk is converted in registers (packed f32x2 math), written to a
-// per-warp 32x32 bf16 staging tile (64B swizzle, conflict-free, two ping-pong buffers) and stored
-// with cp.async.bulk.tensor; the bf16 residual tile is TMA-loaded into the same staging buffer
-// ahead of time and added in place.  (Row-per-thread global stores cost 32 L1 wavefronts per
-// instruction and made the K=768 GEMMs epilogue-bound.)
+// The epilogue is latency-, not throughput-bound (ncu: 2 epilogue warps per scheduler issued 0.19 IPC each and
+// made the K=768 GEMMs epilogue-bound), so it runs 16 warps (4 per scheduler), each owning 32 accumulator rows x
+// BN/4 columns, and fetches everything but the accumulator before it waits for the MMA: per-column constants go
+// to shared memory once per tile and are read back as broadcast 16-byte loads, the bf16 residual tile is
+// TMA-loaded into the warp's staging tile.  Data movement is all TMA: the converted 32 x BN/4 tile is written to
+// the swizzled (conflict-free) staging tile and stored with ONE cp.async.bulk.tensor per warp and tile.
+// (Row-per-thread global stores cost 32 L1 wavefronts per instruction.)
 //
 // Replaces the reference's nn.Dense / einsum projections (layers.py:304-312, :486-488, :483-498).
 #include <cuda.h>
@@ -30,26 +31,36 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumThreads = 384;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kNumEpiWarps = 8;
-constexpr int kStageTileBytes = 32 * 32 * 2;            // one 32x32 bf16 staging tile
+constexpr int kNumEpiWarps = 16;                        // 4 per TMEM lane quarter: each owns 32 rows x BN/4 columns of a tile
+constexpr int kNumEpiThreads = 32 * kNumEpiWarps;
+constexpr int kNumThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);   // 640 -> at most 96 registers per thread
 
 // CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BN tile; 2 = an SM pair per 256 x BN tile, each CTA holding
-// its 128 A rows and HALF of the B rows (BN/2), which halves the per-SM smem fill traffic and allows 6 stages.
-// NBUF = staging tiles per epilogue warp: 2 (ping-pong), or 4 for the residual GEMMs on SM pairs, whose smaller
-// pipeline stages leave room to prefetch the residual tiles of all four column chunks at tile start.
-template <int BN, int CG, int NBUF>
+// its 128 A rows and HALF of the B rows (BN/2), which halves the per-SM smem fill traffic.
+template <int BN, int CG>
 struct Cfg {
   static constexpr int kBRows = BN / CG;                      // B rows resident per CTA
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kNumEpiWarps * NBUF * kStageTileBytes;               // 32 or 64 KB
-  static constexpr int kStages = ((229376 - kStagingBytes) / kStageBytes) > 8 ? 8 : ((229376 - kStagingBytes) / kStageBytes);
+  static constexpr int kColsPerWarp = BN / 4;                 // 64 or 32 output columns per epilogue warp (1 or 2 chunks of 32)
+  static constexpr int kStageTileBytes = 32 * 32 * 2;         // ONE 32 x 32 bf16 staging tile per warp, reused by its chunks
+  static constexpr int kStagingBytes = kNumEpiWarps * kStageTileBytes;          // 32 KB
+  static constexpr int kCvecBytes = BN * 8;                   // {colsum[n], colsum[n+1], bias[n], bias[n+1]} per column pair
+  static constexpr int kRowvecBytes = BM * 8;                 // folded LayerNorm: (rstd, -rstd * mean) per accumulator row
+  static constexpr int kBarBytes = 512;                       // (2*stages + 4 + 16 + 2) mbarriers + the TMEM base pointer
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
-  static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  // The main loop needs ~150 KB of loads in flight per SM (64 B/clk at ~1.5 us of L2/HBM latency), so everything
+  // else is kept small and the rest of the 227 KB is pipeline: 6 stages of 32 KB for SM pairs (5 when the folded
+  // LayerNorm needs its per-row vector).  The stage count is a run-time parameter of the kernel.
+  static constexpr int stages(bool ln) {
+    const int avail = 232448 - kStagingBytes - kCvecBytes - (ln ? kRowvecBytes : 0) - kBarBytes;
+    return (avail / kStageBytes) > 8 ? 8 : (avail / kStageBytes);
+  }
+  static constexpr int smem_bytes(bool ln) {
+    return stages(ln) * kStageBytes + kStagingBytes + kCvecBytes + (ln ? kRowvecBytes : 0) + kBarBytes;
+  }
 };
 
 struct KParams {
@@ -68,27 +79,36 @@ struct KParams {
   float ln_inv_dim;
   float* stats_out;
   int stats_slots;
+  int stages;   // smem ring depth (Cfg::stages)
 };
 
-__device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  constexpr int NBUF = (RESID && CG == 2 && !OUT_F32) ? 4 : 2;
-  using C = Cfg<BN, CG, NBUF>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t staging_base = smem_base + C::kPipeBytes;
-  const uint32_t bar_base = staging_base + C::kStagingBytes;
-  // barriers (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], resid[8 warps][2], then tmem ptr
+  using C = Cfg<BN, CG>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();   // 128B-swizzled tiles need a 1024-byte aligned base (no slack is reserved for realigning)
+  const int kStages = p.stages;
+  const bool ln_fold = p.ln_stats_in != nullptr;
+  const uint32_t staging_base = smem_base + kStages * C::kStageBytes;
+  const uint32_t cvec_base = staging_base + C::kStagingBytes;
+  const uint32_t rowvec_base = cvec_base + C::kCvecBytes;
+  const uint32_t bar_base = rowvec_base + (ln_fold ? C::kRowvecBytes : 0);
+  // barriers (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], resid[16 warps], vec_full, vec_empty, then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  auto resid_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * NBUF + b); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4 + NBUF * kNumEpiWarps);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  auto resid_bar = [&](int w) { return bar_base + 8u * (2 * kStages + 4 + w); };
+  const uint32_t vec_full_bar = bar_base + 8u * (2 * kStages + 4 + kNumEpiWarps);
+  const uint32_t vec_empty_bar = vec_full_bar + 8u;
+  const uint32_t tmem_ptr_addr = vec_empty_bar + 8u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,7 +129,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (RESID) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -117,8 +137,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kNumEpiWarps * CG);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
-    for (int w = 0; w < kNumEpiWarps; ++w)
-      for (int b = 0; b < NBUF; ++b) mbar_init(resid_bar(w, b), 1);
+    for (int w = 0; w < kNumEpiWarps; ++w) mbar_init(resid_bar(w), 1);
+    mbar_init(vec_full_bar, 2);
+    mbar_init(vec_empty_bar, kNumEpiWarps);
     fence_mbar_init();
   }
   if (CG == 2) cluster_sync_all();   // barrier inits of both CTAs are visible before any remote arrive / multicast commit
@@ -154,7 +175,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
             tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n0);
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -186,20 +207,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           if (CG == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (CG == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));  // accumulator complete
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------- vector stagers (64 threads)
+    // Per tile: the per-column constants {colsum, bias} of its BN columns and, for a folded LayerNorm, (rstd,
+    // -rstd * mean) of this CTA's 128 rows.  The global loads of tile i+1 are issued while the epilogue still works
+    // on tile i (their L2/HBM latency used to sit on the epilogue's critical path); the single shared-memory copy is
+    // rewritten once every epilogue warp has released it.
+    const int ht = static_cast<int>(threadIdx.x) - 64;   // 0..63
+    int it = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int n = n0 + ht * 4;
+      if (ht * 4 < BN && n < p.N) {   // N % 8 == 0: groups of 4 columns are all-or-nothing
+        if (ln_fold) cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n));
+        if (p.bias != nullptr) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      }
+      float2 ab[2] = {make_float2(1.f, 0.f), make_float2(1.f, 0.f)};
+      if (ln_fold) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int m = m0 + ht + rr * 64;
+          float2 ss = make_float2(0.f, 0.f);
+          if (m < p.M) {
+            const float2* sp = reinterpret_cast<const float2*>(p.ln_stats_in) + static_cast<size_t>(m) * p.ln_slots;
+            for (int sl = 0; sl < p.ln_slots; ++sl) {   // fixed order: bit-reproducible statistics
+              const float2 t = __ldg(sp + sl);
+              ss.x += t.x; ss.y += t.y;
+            }
+          }
+          const float mean = ss.x * p.ln_inv_dim;
+          const float var = fmaxf(ss.y * p.ln_inv_dim - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + 1e-6f);
+          ab[rr] = make_float2(rstd, -rstd * mean);
+        }
+      }
+      if (it > 0) mbar_wait(vec_empty_bar, (it - 1) & 1u);
+      if (ht * 4 < BN) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cvec_base + ht * 32), "f"(cs.x), "f"(cs.y), "f"(bs.x), "f"(bs.y) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cvec_base + ht * 32 + 16), "f"(cs.z), "f"(cs.w), "f"(bs.z), "f"(bs.w) : "memory");
+      }
+      if (ln_fold) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(rowvec_base + ht * 8), "f"(ab[0].x), "f"(ab[0].y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(rowvec_base + (ht + 64) * 8), "f"(ab[1].x), "f"(ab[1].y) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(vec_full_bar);
+    }
   } else if (warp >= kFirstEpiWarp) {
     // ---------------------------------------------------------------- epilogue
+    // 16 warps: warp (q, slice) owns accumulator rows [32q, 32q+32) (its TMEM lane quarter) x columns
+    // [slice*CW, (slice+1)*CW).  Everything a tile needs besides the accumulator is fetched BEFORE the wait on the
+    // accumulator barrier, so it overlaps the main loop: the per-column constants {colsum, bias} go to shared
+    // memory once per tile (one float per epilogue thread, read back as broadcast 16-byte loads), the folded
+    // LayerNorm's per-row statistics and the residual tile (TMA into the staging buffer) likewise.
     const int e = warp - kFirstEpiWarp;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = e >> 2;         // which half of the BN columns
-    constexpr int kColsPerWarp = BN / 2;
-    constexpr int NCH = kColsPerWarp / 32;
-    const uint32_t stg = staging_base + e * NBUF * kStageTileBytes;
-    uint32_t rphase = 0;   // bit b = parity of residual barrier b
+    const int slice = e >> 2;        // which quarter of the BN columns
+    constexpr int CW = C::kColsPerWarp;
+    constexpr int NCH = CW / 32;
+    const int et = static_cast<int>(threadIdx.x) - kFirstEpiWarp * 32;   // 0..511
+    const uint32_t stg = staging_base + e * C::kStageTileBytes;
+    // 64-byte rows, 16-byte chunk c of row `lane` lives at chunk (c ^ ((lane >> 1) & 3))  (TMA SWIZZLE_64B)
+    const uint32_t rowaddr = stg + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    uint32_t rphase = 0;
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;
@@ -207,78 +285,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int mrow0 = m0 + q * 32;
-      const int ncol0 = n0 + half * kColsPerWarp;
-      if (RESID && !OUT_F32) {
-        // prefetch the residual tiles of the first two chunks into the two staging buffers
-        if (lane == 0) {
-          if (NBUF == 4) {
-            // one buffer per column chunk: the previous tile's four stores were issued in buffer order
-            tma_store_wait_read<3>();
-            mbar_expect_tx(resid_bar(e, 0), kStageTileBytes);
-            tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
-            tma_store_wait_read<2>();
-            mbar_expect_tx(resid_bar(e, 1), kStageTileBytes);
-            tma_load_2d(stg + kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
-            tma_store_wait_read<1>();
-            mbar_expect_tx(resid_bar(e, 2), kStageTileBytes);
-            tma_load_2d(stg + 2 * kStageTileBytes, &tmR, resid_bar(e, 2), ncol0 + 64, mrow0);
-            tma_store_wait_read<0>();
-            mbar_expect_tx(resid_bar(e, 3), kStageTileBytes);
-            tma_load_2d(stg + 3 * kStageTileBytes, &tmR, resid_bar(e, 3), ncol0 + 96, mrow0);
-          } else {
-            tma_store_wait_read<1>();   // the store that last used buffer 0 has drained
-            mbar_expect_tx(resid_bar(e, 0), kStageTileBytes);
-            tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
-            if (NCH > 1) {
-              tma_store_wait_read<0>();
-              mbar_expect_tx(resid_bar(e, 1), kStageTileBytes);
-              tma_load_2d(stg + kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
-            }
-          }
+      const int ncol0 = n0 + slice * CW;
+      if (!OUT_F32 && lane == 0) {
+        tma_store_wait_read<0>();   // the previous tile's last store has finished reading the staging tile
+        if (RESID) {
+          mbar_expect_tx(resid_bar(e), C::kStageTileBytes);
+          tma_load_2d(stg, &tmR, resid_bar(e), ncol0, mrow0);
         }
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int m = mrow0 + lane;
       const bool row_ok = m < p.M;
       const float rscale = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + m) : 1.0f;
-      const f32x2 rscale2 = pk2(rscale, rscale);
       const float* pos_row = nullptr;
       if (p.pos_table != nullptr) pos_row = p.pos_table + static_cast<size_t>(m % p.pos_period) * p.N;
+      mbar_wait(vec_full_bar, it & 1u);   // the stager warps have published this tile's column / row vectors
       // folded LayerNorm of the A rows: v = ln_a * acc + ln_b * colsum[n] + bias[n]
       f32x2 ln_a2 = pk2(1.f, 1.f), ln_b2 = pk2(0.f, 0.f);
-      if (p.ln_stats_in != nullptr) {
-        float2 ss = make_float2(0.f, 0.f);
-        if (row_ok) {
-          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats_in) + static_cast<size_t>(m) * p.ln_slots;
-          for (int sl = 0; sl < p.ln_slots; ++sl) {   // fixed order: bit-reproducible statistics
-            const float2 t = __ldg(sp + sl);
-            ss.x += t.x; ss.y += t.y;
-          }
-        }
-        const float mean = ss.x * p.ln_inv_dim;
-        const float var = fmaxf(ss.y * p.ln_inv_dim - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + 1e-6f);
-        ln_a2 = pk2(rstd, rstd);
-        ln_b2 = pk2(-rstd * mean, -rstd * mean);
+      if (ln_fold) {
+        float a, b;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(rowvec_base + (q * 32 + lane) * 8));
+        ln_a2 = pk2(a, a);
+        ln_b2 = pk2(b, b);
       }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (!OUT_F32 && !RESID) __syncwarp();   // lane 0 saw the staging tile drain
       float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        const int col = half * kColsPerWarp + ch * 32;
-        // bias for this chunk is fetched before the TMEM load so the two latencies overlap
-        float4 bv[8];
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            bv[g] = (n0 + col + g * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float4 cs[8];
-        if (p.ln_stats_in != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            cs[g] = (n0 + col + g * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + col + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const int col = slice * CW + ch * 32;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + col + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
@@ -291,22 +326,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         const int n = n0 + col;
+        const uint32_t cv = cvec_base + col * 8;
         f32x2 v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
-        if (p.ln_stats_in != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            v[2 * g] = fma2(v[2 * g], ln_a2, mul2(pk2(cs[g].x, cs[g].y), ln_b2));
-            v[2 * g + 1] = fma2(v[2 * g + 1], ln_a2, mul2(pk2(cs[g].z, cs[g].w), ln_b2));
-          }
+        for (int i = 0; i < 16; ++i) {
+          float c0, c1, b0, b1;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0), "=f"(c1), "=f"(b0), "=f"(b1) : "r"(cv + i * 16));
+          v[i] = fma2(pk2u(r[2 * i], r[2 * i + 1]), ln_a2, fma2(ln_b2, pk2(c0, c1), pk2(b0, b1)));
         }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            v[2 * g] = add2(v[2 * g], pk2(bv[g].x, bv[g].y));
-            v[2 * g + 1] = add2(v[2 * g + 1], pk2(bv[g].z, bv[g].w));
-          }
+        if (ch == NCH - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(vec_empty_bar);   // this warp no longer reads the tile's column / row vectors
         }
         if (ACT == ACT_GELU) {
 #pragma unroll
@@ -320,6 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (p.row_scale != nullptr) {
+          const f32x2 rscale2 = pk2(rscale, rscale);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = mul2(v[i], rscale2);
         }
@@ -352,29 +383,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else {
-          const int b = (NBUF == 4) ? ch : (ch & 1);
-          const uint32_t buf = stg + b * kStageTileBytes;
-          // 64-byte rows, 16-byte chunk c of row `lane` lives at chunk (c ^ ((lane >> 1) & 3))  (TMA SWIZZLE_64B)
-          const uint32_t rowaddr = buf + lane * 64;
-          const int sw = (lane >> 1) & 3;
           if (RESID) {
-            mbar_wait(resid_bar(e, b), (rphase >> b) & 1u);
-            rphase ^= 1u << b;
+            // chunk 0's residual tile was requested at tile start, chunk 1's right after chunk 0's store (below)
+            mbar_wait(resid_bar(e), rphase);
+            rphase ^= 1u;
+          } else if (ch > 0) {
+            if (lane == 0) tma_store_wait_read<0>();   // chunk 0's store has finished reading the staging tile
+            __syncwarp();
+          }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = rowaddr + ((c ^ sw) << 4);
+            if (RESID) {
               uint32_t w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(rowaddr + ((c ^ sw) << 4)));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
               v[4 * c + 0] = add2(v[4 * c + 0], pk2(bf16_lo(w0), bf16_hi(w0)));
               v[4 * c + 1] = add2(v[4 * c + 1], pk2(bf16_lo(w1), bf16_hi(w1)));
               v[4 * c + 2] = add2(v[4 * c + 2], pk2(bf16_lo(w2), bf16_hi(w2)));
               v[4 * c + 3] = add2(v[4 * c + 3], pk2(bf16_lo(w3), bf16_hi(w3)));
             }
-          } else {
-            if (lane == 0) tma_store_wait_read<1>();   // the store issued two chunks ago (same buffer) has drained
-            __syncwarp();
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -391,26 +418,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
               }
             }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((c ^ sw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, buf, n, mrow0);   // clipped against [M, N] by the tensor map
+            tma_store_2d(&tmC, stg, n, mrow0);   // clipped against [M, N] by the tensor map
             tma_store_commit();
-            if (RESID && NBUF == 2 && ch + 2 < NCH) {
-              // buffer (ch+1)&1 ... is busy; the buffer for chunk ch+2 is this one: wait for the store just issued
-              // to finish reading it, then prefetch that chunk's residual tile
+            if (RESID && ch + 1 < NCH) {
               tma_store_wait_read<0>();
-              mbar_expect_tx(resid_bar(e, b), kStageTileBytes);
-              tma_load_2d(buf, &tmR, resid_bar(e, b), n + 64, mrow0);
+              mbar_expect_tx(resid_bar(e), C::kStageTileBytes);
+              tma_load_2d(stg, &tmR, resid_bar(e), n + 32, mrow0);
             }
           }
           __syncwarp();
         }
       }
       if (!OUT_F32 && p.stats_out != nullptr && row_ok) {
-        const int slot = (tile % num_n_tiles) * 2 + half;
+        const int slot = (tile % num_n_tiles) * 4 + slice;
         reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(m) * p.stats_slots + slot] = make_float2(st_sum, st_sq);
       }
     }
@@ -481,12 +506,14 @@ struct Maps {
 };
 
 template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
-cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp, int grid) {
+cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp_in, int grid) {
   auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32, CG>;
-  constexpr int kSmem = Cfg<BN, CG, (RESID && CG == 2 && !OUT_F32) ? 4 : 2>::kSmemBytes;
+  KParams kp = kp_in;
+  kp.stages = Cfg<BN, CG>::stages(kp.ln_stats_in != nullptr);
+  const int kSmem = Cfg<BN, CG>::smem_bytes(kp.ln_stats_in != nullptr);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -526,7 +553,7 @@ cudaError_t launch_gemm_bn(cudaStream_t s, const Maps& m, const KParams& kp, int
 
 int gemm_stats_slots(int N) {
   const int BN = (N % 256 == 0) ? 256 : 128;
-  return 2 * ((N + BN - 1) / BN);
+  return 4 * ((N + BN - 1) / BN);
 }
 
 cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, int ldb, void* Cout, int ldc, int M, int N,

@@ -174,6 +174,17 @@ class _Module:
     def kernel_launches(self) -> int:
         return int(_lib.lib().vp_kernel_launches(self._handle)) if self._handle is not None else 0
 
+    def trace(self, enable: bool = True) -> None:
+        """Start / stop the in-situ kernel timeline (one CUDA event after every launch; vp_trace)."""
+        _lib.check(_lib.lib().vp_trace(self._ensure_handle(), 1 if enable else 0), self._handle)
+
+    def trace_report(self):
+        """[(label, launches, total_ms)] since trace(True), in first-launch order, plus the ("TOTAL", n, ms) row."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(_lib.lib().vp_trace_report(self._handle, buf, len(buf)), self._handle)
+        rows = [ln.split() for ln in buf.value.decode().splitlines() if ln.strip()]
+        return [(r[0], int(r[1]), float(r[2])) for r in rows]
+
     # -- helpers --------------------------------------------------------------------------------
     @staticmethod
     def _stream_ptr() -> int:
