@@ -155,7 +155,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (elect_one, not lane == 0: ptxas then issues the warp-uniform TMA / tcgen05 instructions directly instead of
+    // wrapping each one in an ELECT / BRA.U.ANY loop)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -181,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -268,6 +270,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // memory once per tile (one float per epilogue thread, read back as broadcast 16-byte loads), the folded
     // LayerNorm's per-row statistics and the residual tile (TMA into the staging buffer) likewise.
     const int e = warp - kFirstEpiWarp;
+    const bool leader = elect_one();   // the one lane of this warp that issues (and later waits for) its TMA operations
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int slice = e >> 2;        // which quarter of the BN columns
     constexpr int CW = C::kColsPerWarp;
@@ -286,7 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int mrow0 = m0 + q * 32;
       const int ncol0 = n0 + slice * CW;
-      if (!OUT_F32 && lane == 0) {
+      if (!OUT_F32 && leader) {
         tma_store_wait_read<0>();   // the previous tile's last store has finished reading the staging tile
         if (RESID) {
           mbar_expect_tx(resid_bar(e), C::kStageTileBytes);
@@ -388,7 +391,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(resid_bar(e), rphase);
             rphase ^= 1u;
           } else if (ch > 0) {
-            if (lane == 0) tma_store_wait_read<0>();   // chunk 0's store has finished reading the staging tile
+            if (leader) tma_store_wait_read<0>();   // chunk 0's store has finished reading the staging tile
             __syncwarp();
           }
 #pragma unroll
@@ -422,7 +425,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (leader) {
             tma_store_2d(&tmC, stg, n, mrow0);   // clipped against [M, N] by the tensor map
             tma_store_commit();
             if (RESID && ch + 1 < NCH) {
@@ -439,7 +442,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(m) * p.stats_slots + slot] = make_float2(st_sum, st_sq);
       }
     }
-    if (!OUT_F32 && lane == 0) tma_store_wait<0>();
+    if (!OUT_F32 && leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
