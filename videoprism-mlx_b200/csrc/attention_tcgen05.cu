@@ -8,14 +8,13 @@
 //                               O = P V   : tcgen05.mma M128 N64 K16 x16, A = P in TMEM, B = V MN-major smem;
 //                               l = P 1   : tcgen05.mma M128 N16 K16 x16 against a tile of ones: the softmax
 //                                           normaliser, summed over exactly the bf16 weights that multiply V)
-//   warp 2      : TMEM allocator
-//   warp 3      : output store (TMA store of a normalised O tile, frees the smem stage)
+//   warps 2, 3, 20, 21 : drain warps (one per TMEM lane quarter): read O and l, normalise, stage bf16 O in the dead Q
+//                 tile, TMA store, free the smem stage (warp 2 also allocates TMEM, warp 3 fills the ones tile)
 //   warps 4..19 : softmax.  Warp (q, c) owns score rows [32q, 32q+32) x key columns [64c, 64c+64) of BOTH query
 //                 tiles; a thread owns one score row.
-// MUFU.EX2 is the bound of this kernel (16 per clock and SM: 4096 clk per problem), so the schedule keeps all 16
-// softmax warps exponentiating ONE query tile at a time while the tensor core works for the other one:
-//     exp(A, keys lo) | drain O(B, previous problem) | exp(A, keys hi) | exp(B, keys lo) | drain O(A) | exp(B, keys hi) | ...
-// PV(A) runs under exp(B, lo), the next problem's S(A) under exp(B, hi), and vice versa.
+// MUFU.EX2 is the bound of this kernel (16 per clock and SM: 4096 clk per problem), so the softmax warps do nothing
+// but exponentiate, ONE query tile at a time, while the tensor core and the drain warps work for the other one:
+//     exp(A) | exp(B) | exp(A') | exp(B') ...    PV(A), drain(A) and the next problem's S(A') all run under exp(B).
 // The scores are read from TMEM exactly once: the logit cap cap*tanh(s/cap) (layers.py:586-594) bounds the exponent
 // (72 in base 2 for cap = 50), so exp2 cannot overflow without a row maximum and softmax is shift-invariant.  The cap is
 // an odd polynomial on the FMA pipe (packed f32x2; MUFU.TANH only for 32-column groups with |s| > cap/2); P is the
@@ -41,7 +40,7 @@ constexpr int kTileBytes = 256 * 64 * 2;        // one of Q / K / V for a proble
 constexpr int kStageBytes = 3 * kTileBytes;     // 96 KB
 constexpr int kStages = 2;
 constexpr int kSoftmaxWarps = 16;
-constexpr int kThreads = 32 * (4 + kSoftmaxWarps);   // 640
+constexpr int kThreads = 32 * (4 + kSoftmaxWarps + 2);   // 704: 4 control/drain warps, 16 softmax warps, 2 more drain warps
 constexpr int kOnesBytes = 2048;   // bf16 1.0 tile: B operand of the row-sum MMA (any 16 x 16 window of it is all ones)
 constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -102,7 +101,7 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       mbar_init(s_full(t), 1);
       mbar_init(p_full(t), kSoftmaxWarps);
       mbar_init(o_full(t), 1);
-      mbar_init(tmem_free(t), kSoftmaxWarps);
+      mbar_init(tmem_free(t), 4);
       for (int q = 0; q < 4; ++q)
         for (int pr = 0; pr < 2; ++pr) mbar_init(rd_done(t, q, pr), 1);
     }
@@ -192,35 +191,68 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         if (it + 1 < n_it) issue_s(1, it + 1);
       }
     }
-  } else if (warp == 3) {
-    // -------------------------------------------------------------- output store: one TMA store per drained O tile
-    // (same order as the softmax warps drain: A(0); then B(it-1), A(it) for it >= 1; finally B(last))
-    const bool leader = elect_one();
-    auto handle = [&](int tile, int it_d) {
-      named_bar_sync(1, 32 * kSoftmaxWarps + 32);   // the normalised bf16 tile is complete in the (dead) Q tile of the stage
-      if (leader) {
-        const int pr = static_cast<int>(blockIdx.x) + it_d * static_cast<int>(gridDim.x);
-        const int frame = pr / p.heads, h = pr % p.heads;
-        const int stage = it_d & 1;
-        const uint32_t so = smem_base + stage * kStageBytes + tile * (kTileBytes / 2);
-        tma_store_2d(&tmO, so, h * 64, frame * 256 + tile * 128);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(empty(stage));   // this tile's share of the stage is dead and its O has left smem
-      }
-      __syncwarp();
-    };
+  } else if (warp == 2 || warp == 3 || warp >= 4 + kSoftmaxWarps) {
+    // -------------------------------------------------------------- drain warps, one per TMEM lane quarter
+    // O = P V and l = P 1 of a (tile, problem) are ready: normalise the 64 output columns of this thread's row, stage them
+    // in the (dead) Q tile of the stage, TMA-store the 128 x 64 tile and release the stage.
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool leader = (warp == 3) && elect_one();
     for (int it = 0; it < n_it; ++it) {
-      if (it > 0) handle(1, it - 1);
-      handle(0, it);
+      const int pr = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      const int frame = pr / p.heads, h = pr % p.heads;
+      const int stage = it & 1;
+#pragma unroll 1
+      for (int tile = 0; tile < 2; ++tile) {
+        const uint32_t T = tmem_base + tile * 256 + lane_off;
+        const uint32_t so = smem_base + stage * kStageBytes + tile * (kTileBytes / 2);
+        const uint32_t rowaddr = so + row * 128;
+        const int sw = row & 7;
+        mbar_wait(o_full(tile), it & 1u);
+        tc_fence_after();
+        uint32_t rs;
+        tmem_ld_32x32b_x1(T + 192, rs);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(T + 64 + 32 * half, o);
+          tmem_ld_wait();
+          if (half == 1) {
+            // everything of this tile has left TMEM: the next problem's S may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_free(tile));
+          }
+          const float inv = 1.0f / __uint_as_float(rs);
+          const f32x2 inv2 = pk2(inv, inv);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float a, b;
+              upk2(mul2(pk2u(o[g * 8 + jj * 2], o[g * 8 + jj * 2 + 1]), inv2), a, b);
+              wv[jj] = pack_bf16x2(a, b);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((4 * half + g) ^ sw) << 4)), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);   // the four drain warps: the tile is complete
+        if (leader) {
+          tma_store_2d(&tmO, so, h * 64, frame * 256 + tile * 128);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(empty(stage));   // this tile's share of the stage is dead and its O has left smem
+        }
+      }
     }
-    if (n_it > 0) handle(1, n_it - 1);
     if (leader) tma_store_wait<0>();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kSoftmaxWarps) {
     // -------------------------------------------------------------- softmax warps: (lane quarter q, key slice c)
     const int q = warp & 3;
     const int c = (warp - 4) >> 2;
-    const int row = q * 32 + lane;                        // row inside a 128-row query tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int scol = 64 * c;                              // this warp's 64 score columns
     const int pcol = (c >> 1) * 128 + (c & 1) * 32;       // where its 32 columns of bf16 P go
@@ -265,7 +297,7 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     };
     // Even slices store each chunk's P at once (over their own consumed columns).  Odd slices write over columns the
     // even slice of their pair reads as its SECOND chunk, so they keep the first chunk's P in registers and store both
-    // once that read is done (the wait sits after the drain's CTA-wide barrier on both sides: no circular wait).
+    // once that read is done.
     auto p_store = [&](int tile, int j, const uint32_t (&w)[16]) {
       tmem_st_32x32b_x16(tmem_base + tile * 256 + lane_off + pcol + 16 * j, w);
     };
@@ -289,39 +321,6 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(tile));
     };
-    // O = P V and l = P 1 of (tile, problem it_d) are ready: normalise 16 output columns, stage them in the dead Q tile
-    auto drain = [&](int tile, int it_d) {
-      const uint32_t T = tmem_base + tile * 256 + lane_off;
-      mbar_wait(o_full(tile), it_d & 1u);
-      tc_fence_after();
-      uint32_t o[16];
-      uint32_t rs;
-      tmem_ld_32x32b_x16(T + 64 + 16 * c, o);
-      tmem_ld_32x32b_x1(T + 192, rs);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_free(tile));
-      const float inv = 1.0f / __uint_as_float(rs);
-      const f32x2 inv2 = pk2(inv, inv);
-      const uint32_t so = smem_base + (it_d & 1) * kStageBytes + tile * (kTileBytes / 2);
-      const uint32_t rowaddr = so + row * 128;
-      const int sw = row & 7;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t wv[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float a, b;
-          upk2(mul2(pk2u(o[g * 8 + jj * 2], o[g * 8 + jj * 2 + 1]), inv2), a, b);
-          wv[jj] = pack_bf16x2(a, b);
-        }
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((2 * c + g) ^ sw) << 4)), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 32 * kSoftmaxWarps + 32);   // hands the tile to the store warp
-    };
-
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1u;
       // ---- query tile A
@@ -329,18 +328,15 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       tc_fence_after();
       uint32_t w0[16];
       exp_first(0, w0);
-      if (it > 0) drain(1, it - 1);
       exp_second(0, ph, w0);
       p_done(0);
       // ---- query tile B
       mbar_wait(s_full(1), ph);
       tc_fence_after();
       exp_first(1, w0);
-      drain(0, it);
       exp_second(1, ph, w0);
       p_done(1);
     }
-    if (n_it > 0) drain(1, n_it - 1);
   }
 
   tc_fence_before();
