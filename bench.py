@@ -6,7 +6,9 @@
 
 Workload (BASELINE.json configs[1]): videoprism_public_v1_base, batch 32 synthetic clips, bf16 tensor-core
 math with fp32 accumulation, the batch sharded contiguously over the N GPUs of one node (32/N clips per
-rank, no inter-GPU traffic inside the encoder).  One "step" = one forward of the whole batch.
+rank, no inter-GPU traffic inside the encoder: "scaling": "strong", the config as BASELINE.json states it).
+`--scaling weak` keeps 32 clips on EVERY rank instead (global batch 32*N).  One "step" = one forward of the
+whole batch.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM), `e2e` is the
 same metric through the public API with host buffers (H2D of the clips and D2H of the features inside the
@@ -211,6 +213,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="base", choices=["base", "large"])
     ap.add_argument("--global-batch", type=int, default=32)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --global-batch clips in total, sharded over the ranks (BASELINE configs[1]); "
+                         "weak: --global-batch clips on every rank")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "retrieval"],
                     help="encoder: BASELINE configs 2/3 (default); retrieval: configs 4/5 (LvT video+text, all-gather, similarity)")
     ap.add_argument("--global-queries", type=int, default=1024)
@@ -245,9 +250,13 @@ def main():
     state = vp.synthetic_state(model, seed=1234)
     model.load_state(state)
 
-    if args.global_batch % world:
-        raise SystemExit("--global-batch must be divisible by the number of GPUs")
-    b_local = args.global_batch // world
+    if args.scaling == "weak":
+        b_local = args.global_batch
+        args.global_batch = b_local * world
+    else:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        b_local = args.global_batch // world
     T, S = 16, 288
     # rotate device input buffers so the clips read by consecutive steps never sit in the 126 MB L2
     clip_bytes = T * S * S * 3 * 4
@@ -326,53 +335,55 @@ def main():
         e2e["uint8_frames"] = {"value": args.global_batch * n_e2e / float(tt.item()), "unit": "clips/s",
                                "h2d_bytes_per_step": b_local * clip_bytes // 4, "d2h_bytes_per_step": out_bytes}
 
-    # ---- roofline of the dominant kernel (FFN1 GEMM + GELU epilogue), CUDA events on the launch stream
+    # ---- roofline of the dominant kernel (FFN1 GEMM: folded LayerNorm + GELU epilogue), timed IN SITU: the engine
+    # records a CUDA event after every launch on the launch stream (vp_trace), a few more steps of the same workload
+    # run with that switched on, and the kernel's duration is the event-to-event time averaged over its launches
+    # (warm L2, sustained power-capped clocks: the state it has inside the timed region above).
     peaks, peak_src = measured_peaks()
     roof = None
     if rank == 0:
-        import videoprism_b200._lib as L
-        lib = L.lib()
         D, F = model.config["model_dim"], model.config["mlp_dim"]
         M = b_local * T * 256
-        A = (torch.randn((M, D), device="cuda") * 0.5).bfloat16()
-        Wt = (torch.randn((F, D), device="cuda") * 0.02).bfloat16()
-        bias = torch.zeros((F,), device="cuda")
-        Cm = torch.empty((M, F), dtype=torch.bfloat16, device="cuda")
-        st = int(torch.cuda.current_stream().cuda_stream)
-        def gemm():
-            rc = lib.vp_gemm_bf16(A.data_ptr(), D, Wt.data_ptr(), D, Cm.data_ptr(), F, M, F, D, bias.data_ptr(), 1, None, 0, None, None, 0, 0, st)
-            assert rc == 0
-        for _ in range(3):
-            gemm()
-        torch.cuda.synchronize()
-        reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            gemm()
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
+        n_trace = max(2, min(args.steps, 5))
+        model.trace(True)
+        for i in range(n_trace):
+            step(i)
+        rows = model.trace_report()
+        model.trace(False)
+        total_ms = [r for r in rows if r[0] == "TOTAL"][0][2]
+        ffn1 = [r for r in rows if r[0].endswith(".ffn1")]
+        k_ms = sum(r[2] for r in ffn1) / sum(r[1] for r in ffn1)
+        shares = {r[0]: round(r[2] / total_ms, 4) for r in rows if r[0] != "TOTAL"}
         flops = 2.0 * M * F * D
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         fwd_tf = value / world * GF_PER_CLIP[args.model] / 1e3
-        roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel<256,GELU> FFN1 [{M}x{D}]x[{D}x{F}]", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src + ", bf16_tflops_sustained",
-                "ms_per_launch": k_ms, "flops_per_launch": flops,
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"ffn1_ln_gelu_{M}x{F}x{D}")
+        roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel<256,GELU> FFN1 (LayerNorm folded) [{M}x{D}]x[{D}x{F}]", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src + ", bf16_tflops_sustained",
+                "ms_per_launch": k_ms, "flops_per_launch": flops, "launches_timed": sum(r[1] for r in ffn1),
+                "share_of_step": round(sum(r[2] for r in ffn1) / total_ms, 4),
+                "how": "CUDA events after every launch on the launch stream (vp_trace), averaged over the kernel's launches in "
+                       f"{n_trace} extra steps of the same workload",
+                "kernel_shares": shares,
                 "forward": {"achieved": fwd_tf, "frac": fwd_tf / peak, "gflop_per_clip": GF_PER_CLIP[args.model],
                             "note": "whole forward per GPU = clips/s/GPU x algorithmic GF/clip"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, n_steps, threads, mean = cpu_oracle_clips_per_s(args.model, 1, 0, budget_s=60.0)
+        v, n_steps, threads, mean = cpu_oracle_clips_per_s(args.model, 10, 1, budget_s=25.0)
         cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
-               "sample": f"1 clip (1x16x288x288x3), {n_steps} run, {mean:.2f} s; fp32 PyTorch-CPU restatement of the Flax path (oracle/)"}
+               "sample": f"1 clip (1x16x288x288x3) per run, 1 warm-up + {n_steps} timed runs (<= 25 s of CPU work), mean {mean:.2f} s; "
+                         "fp32 PyTorch-CPU restatement of the Flax path (oracle/), all host threads torch uses"}
 
     if rank == 0:
         line = {
             "metric": "clips/sec (16x288^2 encoder forward)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{name} encoder forward, 16x288x288x3 clips, random-init weights", "global_batch": args.global_batch,
                        "clips_per_gpu": b_local, "parallelism": f"dp{world} (batch shard, no collective)",

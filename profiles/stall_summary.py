@@ -12,7 +12,11 @@ top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h = rows[1]
-data = [r for r in rows[2:] if len(r) == len(h)]
+data = []
+for r in rows[2:]:
+    if len(r) != len(h) or r[0] == "Address":   # a second kernel of the report starts: only the first one is summarised
+        break
+    data.append(r)
 ia, isrc, isamp, iex = h.index("Address"), h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
 stall = [i for i, k in enumerate(h) if k.startswith("stall_") and "Not Issued" not in k]
 base = int(data[0][ia], 16)

@@ -215,3 +215,26 @@ def test_errors_mirror_reference():
     bad.pop("params/temporal_ln/bias")
     with pytest.raises(KeyError):
         make_model(cfg).apply(bad, np.zeros((1, 4, 16, 16, 3), np.float32))
+
+
+def test_trace_accounts_for_every_launch_and_leaves_results_unchanged():
+    """vp_trace: one event per launch, labels of the path's stages, total launch count equal to vp_kernel_launches,
+    and a traced forward is bitwise equal to an untraced one."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    m = vp.get_model("videoprism_public_v1_base")
+    m.load_state(O.make_synthetic_weights(cfg))
+    v = torch.from_numpy(O.make_video(2, 16, 288, seed=3)).cuda()
+    plain, _ = m(v)
+    n0 = m.kernel_launches
+    m.trace(True)
+    traced, _ = m(v)
+    rows = m.trace_report()
+    m.trace(False)
+    per_forward = m.kernel_launches - n0
+    labels = {r[0]: r for r in rows}
+    assert labels["TOTAL"][1] == per_forward == 84
+    for k, n in (("patchify", 1), ("patch_proj", 1), ("spatial.qkv", 12), ("spatial.attn", 12), ("spatial.ffn1", 12),
+                 ("temporal.ffn2", 4), ("spatial_ln", 1), ("temporal_ln", 1)):
+        assert labels[k][1] == n and labels[k][2] > 0.0
+    assert torch.equal(plain, traced)

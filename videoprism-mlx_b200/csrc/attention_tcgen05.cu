@@ -33,6 +33,7 @@ namespace vp {
 bool make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                        uint32_t box_cols, int swizzle_bytes);
 int num_sms();
+bool pdl_enabled();
 
 namespace {
 
@@ -121,6 +122,8 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  pdl_launch_dependents();   // the setup above overlapped the tail of the previous kernel (the QKV GEMM); its output is read below
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -383,8 +386,16 @@ cudaError_t launch_attention_tcgen05(cudaStream_t s, const AttnArgs& a) {
     attr_done = true;
   }
   const int grid = p.num_problems < num_sms() ? p.num_problems : num_sms();
-  attn256_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(tq, to, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attn256_tcgen05_kernel, tq, to, p);
 }
 
 }  // namespace vp

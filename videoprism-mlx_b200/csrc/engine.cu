@@ -797,8 +797,31 @@ static int encoder_forward_host_impl(vp_handle* h, const void* video_v, int in_d
   const size_t clip_in = (size_t)T * H * W * 3;
   const size_t N = (size_t)(H / h->cfg.patch_size) * (W / h->cfg.patch_size);
   const size_t clip_out = (size_t)T * N * h->cfg.model_dim;
-  const int chunk = h->host_chunk_clips > 0 ? h->host_chunk_clips : (B >= 16 ? 8 : (B >= 4 ? (B + 1) / 2 : B));
-  const int nchunks = (B + chunk - 1) / chunk;
+  // Chunk schedule.  Only the first chunk's H2D and the last chunk's D2H are exposed (everything else overlaps the
+  // forward of a neighbouring chunk), so both ends are small (2 clips); every chunk costs ~0.4 ms of fixed per-launch
+  // overhead (84 launches), so the middle runs 8-clip chunks with 6-clip ramps: 32 clips -> 2 6 8 8 6 2.
+  std::vector<int> sizes;
+  if (h->host_chunk_clips > 0) {
+    for (int c0 = 0; c0 < B; c0 += h->host_chunk_clips) sizes.push_back(B - c0 < h->host_chunk_clips ? B - c0 : h->host_chunk_clips);
+  } else if (B <= 4) {
+    for (int c0 = 0; c0 < B; c0 += 2) sizes.push_back(B - c0 < 2 ? B - c0 : 2);
+  } else {
+    const int R = B - 4;   // between the two 2-clip end chunks
+    sizes.push_back(2);
+    if (R <= 8) {
+      sizes.push_back(R);
+    } else {
+      const int n8 = R >= 12 ? (R - 12) / 8 : 0;
+      const int rem = R - 8 * n8;
+      sizes.push_back(rem / 2);
+      for (int i = 0; i < n8; ++i) sizes.push_back(8);
+      sizes.push_back(rem - rem / 2);
+    }
+    sizes.push_back(2);
+  }
+  const int nchunks = (int)sizes.size();
+  int chunk = 0;
+  for (int c : sizes) chunk = c > chunk ? c : chunk;
   const size_t in_stride = ((size_t)chunk * clip_in * esz + 255) / 256 * 256;
   const size_t out_stride = ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256;
   const size_t pad_bytes = frame_paddings ? (size_t)B * T * sizeof(float) : 0;
@@ -815,10 +838,10 @@ static int encoder_forward_host_impl(vp_handle* h, const void* video_v, int in_d
   CK(cudaEventRecord(h->ev_start, st));
   CK(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
   CK(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
-  for (int i = 0; i < nchunks; ++i) {
+  int c0 = 0;
+  for (int i = 0; i < nchunks; c0 += sizes[i], ++i) {
     const int b = i & 1;
-    const int c0 = i * chunk;
-    const int bc = (B - c0) < chunk ? (B - c0) : chunk;
+    const int bc = sizes[i];
     float* d_in = reinterpret_cast<float*>(in_base + b * in_stride);
     float* d_out = reinterpret_cast<float*>(out_base + b * out_stride);
     float* d_sp = spatial_features ? reinterpret_cast<float*>(out_base + (2 + b) * out_stride) : nullptr;

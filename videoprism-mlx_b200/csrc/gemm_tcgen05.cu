@@ -152,6 +152,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous kernel
+  // in the stream; from here on its output is read.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -491,6 +495,11 @@ bool make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("VP_PDL") && atoi(getenv("VP_PDL")) == 0);
+  return on;
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -520,19 +529,24 @@ cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp_in, i
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  if (CG == 1) {
-    kern<<<grid, kNumThreads, kSmem, s>>>(m.a, m.b, m.c, m.r, kp);
-    return cudaGetLastError();
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {   // programmatic dependent launch: the prologue overlaps the previous kernel's tail (ptx.cuh: pdl_wait)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.c, m.r, kp);
 }
 
