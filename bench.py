@@ -100,6 +100,12 @@ def cpu_oracle_clips_per_s(model: str, steps: int, warmup: int, budget_s: float)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import videoprism_oracle as O
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would make this a 1-thread run)
+    try:
+        n_cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_cores))
     cfg = O.CONFIGS[MODEL_NAME[model]]
     W = O.to_torch(O.make_synthetic_weights(cfg))
     v = torch.from_numpy(O.make_video(1, 16, 288, seed=0))

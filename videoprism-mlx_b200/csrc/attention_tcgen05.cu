@@ -285,9 +285,28 @@ attn256_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           const f32x2 u = mul2(v, v);
           f32x2 t = fma2(u, B2, B1);
           t = fma2(t, u, B0);
-          float a, b;
-          upk2(mul2(t, v), a, b);
-          w[i] = __byte_perm(__float_as_uint(ex2_approx(a)), __float_as_uint(ex2_approx(b)), 0x7632);
+          const f32x2 x = mul2(t, v);   // capped logit, base-2 exponent, |x| <= 72.2
+          if ((i & 3) == 3) {
+            // every 4th pair takes exp2 on the FMA / ALU pipes instead of MUFU (the kernel's bound): round-to-nearest
+            // split x = n + f by the 1.5*2^23 trick, 2^f by a cubic (relative error 1.0e-4, a 40th of the bf16 step of P),
+            // n added into the exponent field
+            const f32x2 tt = add2(x, pk2(12582912.f, 12582912.f));
+            const f32x2 nn = add2(tt, pk2(-12582912.f, -12582912.f));
+            const f32x2 fr = fma2(nn, pk2(-1.f, -1.f), x);
+            f32x2 pp = fma2(fr, pk2(0.055008938f, 0.055008938f), pk2(0.24221096f, 0.24221096f));
+            pp = fma2(pp, fr, pk2(0.69328293f, 0.69328293f));
+            pp = fma2(pp, fr, pk2(1.f, 1.f));
+            float ta, tb, pa, pb;
+            upk2(tt, ta, tb);
+            upk2(pp, pa, pb);
+            const uint32_t ea = __float_as_uint(pa) + (__float_as_uint(ta) << 23);
+            const uint32_t eb = __float_as_uint(pb) + (__float_as_uint(tb) << 23);
+            w[i] = __byte_perm(ea, eb, 0x7632);
+          } else {
+            float a, b;
+            upk2(x, a, b);
+            w[i] = __byte_perm(__float_as_uint(ex2_approx(a)), __float_as_uint(ex2_approx(b)), 0x7632);
+          }
         }
       } else {
 #pragma unroll
