@@ -670,6 +670,7 @@ void vp_destroy(vp_handle* h) {
   if (h == nullptr) return;
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
+  for (auto& t : h->trace) cudaEventDestroy(t.second);
 
   if (h->d_spatial_pos) cudaFree(h->d_spatial_pos);
   if (h->d_temporal_pos) cudaFree(h->d_temporal_pos);

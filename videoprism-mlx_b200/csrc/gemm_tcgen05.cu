@@ -33,7 +33,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kNumEpiWarps = 16;                        // 4 per TMEM lane quarter: each owns 32 rows x BN/4 columns of a tile
-constexpr int kNumEpiThreads = 32 * kNumEpiWarps;
 constexpr int kNumThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);   // 640 -> at most 96 registers per thread
 
 // CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BN tile; 2 = an SM pair per 256 x BN tile, each CTA holding
@@ -45,8 +44,10 @@ struct Cfg {
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColsPerWarp = BN / 4;                 // 64 or 32 output columns per epilogue warp (1 or 2 chunks of 32)
-  static constexpr int kStageTileBytes = 32 * 32 * 2;         // ONE 32 x 32 bf16 staging tile per warp, reused by its chunks
-  static constexpr int kStagingBytes = kNumEpiWarps * kStageTileBytes;          // 32 KB
+  static constexpr int kStageTileBytes = 32 * 32 * 2;         // 32 x 32 bf16 staging tile
+  // staging tiles per epilogue warp (run-time, KParams::nbuf): 1, reused by the warp's chunks (32 KB in all), or 2 for
+  // short-K residual GEMMs, whose residual tiles are then all requested at tile start (64 KB, one pipeline stage less)
+  static constexpr int staging_bytes(int nbuf) { return kNumEpiWarps * nbuf * kStageTileBytes; }
   static constexpr int kCvecBytes = BN * 8;                   // {colsum[n], colsum[n+1], bias[n], bias[n+1]} per column pair
   static constexpr int kRowvecBytes = BM * 8;                 // folded LayerNorm: (rstd, -rstd * mean) per accumulator row
   static constexpr int kBarBytes = 512;                       // (2*stages + 4 + 16 + 2) mbarriers + the TMEM base pointer
@@ -54,12 +55,12 @@ struct Cfg {
   // The main loop needs ~150 KB of loads in flight per SM (64 B/clk at ~1.5 us of L2/HBM latency), so everything
   // else is kept small and the rest of the 227 KB is pipeline: 6 stages of 32 KB for SM pairs (5 when the folded
   // LayerNorm needs its per-row vector).  The stage count is a run-time parameter of the kernel.
-  static constexpr int stages(bool ln) {
-    const int avail = 232448 - kStagingBytes - kCvecBytes - (ln ? kRowvecBytes : 0) - kBarBytes;
+  static constexpr int stages(bool ln, int nbuf) {
+    const int avail = 232448 - staging_bytes(nbuf) - kCvecBytes - (ln ? kRowvecBytes : 0) - kBarBytes;
     return (avail / kStageBytes) > 8 ? 8 : (avail / kStageBytes);
   }
-  static constexpr int smem_bytes(bool ln) {
-    return stages(ln) * kStageBytes + kStagingBytes + kCvecBytes + (ln ? kRowvecBytes : 0) + kBarBytes;
+  static constexpr int smem_bytes(bool ln, int nbuf) {
+    return stages(ln, nbuf) * kStageBytes + staging_bytes(nbuf) + kCvecBytes + (ln ? kRowvecBytes : 0) + kBarBytes;
   }
 };
 
@@ -80,11 +81,8 @@ struct KParams {
   float* stats_out;
   int stats_slots;
   int stages;   // smem ring depth (Cfg::stages)
+  int nbuf;     // staging tiles per epilogue warp (1 or 2)
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -97,16 +95,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int kStages = p.stages;
   const bool ln_fold = p.ln_stats_in != nullptr;
   const uint32_t staging_base = smem_base + kStages * C::kStageBytes;
-  const uint32_t cvec_base = staging_base + C::kStagingBytes;
+  const uint32_t cvec_base = staging_base + C::staging_bytes(p.nbuf);
   const uint32_t rowvec_base = cvec_base + C::kCvecBytes;
   const uint32_t bar_base = rowvec_base + (ln_fold ? C::kRowvecBytes : 0);
-  // barriers (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], resid[16 warps], vec_full, vec_empty, then tmem ptr
+  // barriers (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], resid[16 warps][2], vec_full, vec_empty, then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  auto resid_bar = [&](int w) { return bar_base + 8u * (2 * kStages + 4 + w); };
-  const uint32_t vec_full_bar = bar_base + 8u * (2 * kStages + 4 + kNumEpiWarps);
+  auto resid_bar = [&](int w, int b) { return bar_base + 8u * (2 * kStages + 4 + 2 * w + b); };
+  const uint32_t vec_full_bar = bar_base + 8u * (2 * kStages + 4 + 2 * kNumEpiWarps);
   const uint32_t vec_empty_bar = vec_full_bar + 8u;
   const uint32_t tmem_ptr_addr = vec_empty_bar + 8u;
 
@@ -137,7 +135,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kNumEpiWarps * CG);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
-    for (int w = 0; w < kNumEpiWarps; ++w) mbar_init(resid_bar(w), 1);
+    for (int w = 0; w < kNumEpiWarps; ++w) { mbar_init(resid_bar(w, 0), 1); mbar_init(resid_bar(w, 1), 1); }
     mbar_init(vec_full_bar, 2);
     mbar_init(vec_empty_bar, kNumEpiWarps);
     fence_mbar_init();
@@ -279,8 +277,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int slice = e >> 2;        // which quarter of the BN columns
     constexpr int CW = C::kColsPerWarp;
     constexpr int NCH = CW / 32;
-    const int et = static_cast<int>(threadIdx.x) - kFirstEpiWarp * 32;   // 0..511
-    const uint32_t stg = staging_base + e * C::kStageTileBytes;
+    const bool two_bufs = p.nbuf == 2;   // chunk ch of a tile uses staging tile ch (else all chunks share tile 0)
+    const uint32_t stg = staging_base + e * p.nbuf * C::kStageTileBytes;
     // 64-byte rows, 16-byte chunk c of row `lane` lives at chunk (c ^ ((lane >> 1) & 3))  (TMA SWIZZLE_64B)
     const uint32_t rowaddr = stg + lane * 64;
     const int sw = (lane >> 1) & 3;
@@ -296,8 +294,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!OUT_F32 && leader) {
         tma_store_wait_read<0>();   // the previous tile's last store has finished reading the staging tile
         if (RESID) {
-          mbar_expect_tx(resid_bar(e), C::kStageTileBytes);
-          tma_load_2d(stg, &tmR, resid_bar(e), ncol0, mrow0);
+          mbar_expect_tx(resid_bar(e, 0), C::kStageTileBytes);
+          tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
+          if (two_bufs && NCH > 1) {
+            mbar_expect_tx(resid_bar(e, 1), C::kStageTileBytes);
+            tma_load_2d(stg + C::kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
+          }
         }
       }
       const int m = mrow0 + lane;
@@ -390,17 +392,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else {
+          const int bsel = (two_bufs && ch > 0) ? 1 : 0;
+          const uint32_t boff = bsel * C::kStageTileBytes;
           if (RESID) {
-            // chunk 0's residual tile was requested at tile start, chunk 1's right after chunk 0's store (below)
-            mbar_wait(resid_bar(e), rphase);
-            rphase ^= 1u;
-          } else if (ch > 0) {
+            // chunk 0's residual tile was requested at tile start; chunk 1's too when it has its own staging tile,
+            // else right after chunk 0's store (below)
+            mbar_wait(resid_bar(e, bsel), (rphase >> bsel) & 1u);
+            rphase ^= 1u << bsel;
+          } else if (ch > 0 && !two_bufs) {
             if (leader) tma_store_wait_read<0>();   // chunk 0's store has finished reading the staging tile
             __syncwarp();
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t addr = rowaddr + ((c ^ sw) << 4);
+            const uint32_t addr = rowaddr + boff + ((c ^ sw) << 4);
             if (RESID) {
               uint32_t w0, w1, w2, w3;
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
@@ -430,12 +435,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (leader) {
-            tma_store_2d(&tmC, stg, n, mrow0);   // clipped against [M, N] by the tensor map
+            tma_store_2d(&tmC, stg + boff, n, mrow0);   // clipped against [M, N] by the tensor map
             tma_store_commit();
-            if (RESID && ch + 1 < NCH) {
+            if (RESID && !two_bufs && ch + 1 < NCH) {
               tma_store_wait_read<0>();
-              mbar_expect_tx(resid_bar(e), C::kStageTileBytes);
-              tma_load_2d(stg, &tmR, resid_bar(e), n + 32, mrow0);
+              mbar_expect_tx(resid_bar(e, 0), C::kStageTileBytes);
+              tma_load_2d(stg, &tmR, resid_bar(e, 0), n + 32, mrow0);
             }
           }
           __syncwarp();
@@ -521,8 +526,12 @@ template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp_in, int grid) {
   auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32, CG>;
   KParams kp = kp_in;
-  kp.stages = Cfg<BN, CG>::stages(kp.ln_stats_in != nullptr);
-  const int kSmem = Cfg<BN, CG>::smem_bytes(kp.ln_stats_in != nullptr);
+  // A second staging tile per warp (all residual tiles of a tile requested at its start, one pipeline stage less) was
+  // measured neutral for the out-projection (178 vs 175 us in situ): off unless VP_GEMM_NBUF=2.
+  static const int nbuf_env = getenv("VP_GEMM_NBUF") ? atoi(getenv("VP_GEMM_NBUF")) : 1;
+  kp.nbuf = (nbuf_env == 2 && RESID && !OUT_F32 && BN == 256 && kp.K <= 1024) ? 2 : 1;
+  kp.stages = Cfg<BN, CG>::stages(kp.ln_stats_in != nullptr, kp.nbuf);
+  const int kSmem = Cfg<BN, CG>::smem_bytes(kp.ln_stats_in != nullptr, kp.nbuf);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
