@@ -139,3 +139,8 @@ ms, tf = attention(B * N, T, N)
 print(f"attention temporal: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s   ({(4.0*M*D*2)/ms/1e6:.0f} GB/s algorithmic)")
 ms, gbs = layernorm()
 print(f"layernorm [{M},{D}]: {ms*1e3:8.1f} us  {gbs:7.0f} GB/s")
+if model == "base":
+    ms, tf = attention(B // 8 if B >= 8 else 1, T * N, 1)
+    print(f"attention auxiliary S=4096 (tcgen05 key loop), {max(B // 8, 1)} clips: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+    ms, tf = attention(B // 8 if B >= 8 else 1, T * N, 1, force=1)
+    print(f"attention auxiliary S=4096 (mma.sync flash), {max(B // 8, 1)} clips: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")

@@ -236,7 +236,10 @@ def ref_attention(qkv, num_seq, S, group, heads, dh, cap, key_pad, causal):
     (2 * 256, 16, 256, 12, 64, 0, False),  # temporal stack: tubes strided by N=256
     (2 * 16, 8, 16, 2, 32, 0, True),    # temporal, T=8, dh=32, frame paddings
     (6, 65, 1, 12, 64, 1, True),        # text tower: causal + paddings, ragged S
-    (2, 1024, 1, 4, 64, 0, False),      # auxiliary-style long sequence
+    (2, 1024, 1, 4, 64, 0, False),      # auxiliary-style long sequence (tcgen05 key-loop kernel, one problem per CTA)
+    (3, 4096, 1, 12, 64, 0, False),     # auxiliary encoder shape: 576 problems, 32 key blocks each (persistent loop, phases)
+    (1, 512, 1, 2, 64, 0, False),       # shortest sequence of the key-loop kernel
+    (2, 1024, 1, 4, 64, 2, False),      # the same long sequence on the mma.sync flash kernel
     (3, 16, 1, 2, 32, 0, True),
     (5, 100, 1, 2, 32, 1, True),
 ])
@@ -246,8 +249,8 @@ def test_attention(L, num_seq, S, group, heads, dh, causal, pad):
     rows = num_seq * S
     qkv = torch.randn((rows, 3 * D), device="cuda", generator=g)
     qkv[:, :D] *= 1.5          # logits of a few units .. tens: exercises the tanh cap
-    if num_seq == 8 and S == 256:
-        qkv[:256, :D] *= 4     # first frame: |logits| well beyond cap/2 -> the MUFU.TANH slow path of the tcgen05 kernel
+    if (num_seq == 8 and S == 256) or S == 1024:
+        qkv[:256, :D] *= 4     # first rows: |logits| well beyond cap/2 -> the MUFU.TANH slow path of the tcgen05 kernels
     qkv = qkv.bfloat16()
     key_pad = None
     if pad:

@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const AttnArgs a, int t
 }  // namespace
 
 cudaError_t launch_attention_tcgen05(cudaStream_t s, const AttnArgs& a);
+cudaError_t launch_attention_long_tcgen05(cudaStream_t s, const AttnArgs& a);
 
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (a.num_seq <= 0 || a.S <= 0) return cudaSuccess;
@@ -314,6 +315,8 @@ cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (!a.force_mma_sync) {
     const cudaError_t e = launch_attention_tcgen05(s, a);   // S = 256, dh = 64, unmasked: the spatial stack
     if (e != cudaErrorNotSupported) return e;
+    const cudaError_t e2 = launch_attention_long_tcgen05(s, a);   // S = 512, 768, ... unmasked: the auxiliary encoder (S = 4096)
+    if (e2 != cudaErrorNotSupported) return e2;
   }
   if (a.S <= 16) {
     const int total = a.num_seq * a.heads;
