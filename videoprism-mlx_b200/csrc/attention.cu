@@ -10,6 +10,8 @@
 // S=256 spatial case lives in attention_tcgen05.cu.
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
