@@ -101,6 +101,7 @@ struct vp_handle {
   bf16* w_patch = nullptr; float* b_patch = nullptr; int k_patch = 0, k_patch_pad = 0;
   std::vector<float> h_spatial_pos, h_temporal_pos;  // host copies for (re)interpolation
   float* d_spatial_pos = nullptr; int spatial_grid_h = 0, spatial_grid_w = 0;
+  bf16* d_spatial_pos_bf16 = nullptr;   // the same table in bf16: TMA-loaded like a residual tile by the patch projection
   float* d_temporal_pos = nullptr; int temporal_len = 0;
   StackWeights spatial, temporal, aux, text;
   std::vector<StackWeights*> stacks;   // the stacks this model has (for finalize_stack)
@@ -394,6 +395,11 @@ int prepare_pos_tables(vp_handle* h, int T, int gh, int gw, cudaStream_t st) {
     if (h->d_spatial_pos) { cudaFree(h->d_spatial_pos); h->d_spatial_pos = nullptr; }
     CK(cudaMalloc(&h->d_spatial_pos, tab.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->d_spatial_pos, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    std::vector<bf16> tab16(tab.size());
+    for (size_t i = 0; i < tab.size(); ++i) tab16[i] = __float2bfloat16(tab[i]);
+    if (h->d_spatial_pos_bf16) { cudaFree(h->d_spatial_pos_bf16); h->d_spatial_pos_bf16 = nullptr; }
+    CK(cudaMalloc(&h->d_spatial_pos_bf16, tab16.size() * sizeof(bf16)));
+    CK(cudaMemcpyAsync(h->d_spatial_pos_bf16, tab16.data(), tab16.size() * sizeof(bf16), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     h->spatial_grid_h = gh; h->spatial_grid_w = gw;
   }
@@ -593,7 +599,12 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
   float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
   float* stats_b = h->fuse_ln ? stats_a + h->stats_stride : nullptr;
   vp::GemmEpilogue ep;
-  ep.bias = h->b_patch; ep.pos_table = h->d_spatial_pos; ep.pos_period = N;
+  ep.bias = h->b_patch;
+  if (N % 32 == 0) {   // tiles of 32 rows never straddle a frame: the position rows of a tile are one TMA box of the bf16 table
+    ep.resid = h->d_spatial_pos_bf16; ep.ldr = D; ep.resid_period = N;
+  } else {
+    ep.pos_table = h->d_spatial_pos; ep.pos_period = N;
+  }
   ep.stats_out = stats_a;
   CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->mark(st, "patch_proj");
 
@@ -673,6 +684,7 @@ void vp_destroy(vp_handle* h) {
   for (auto& t : h->trace) cudaEventDestroy(t.second);
 
   if (h->d_spatial_pos) cudaFree(h->d_spatial_pos);
+  if (h->d_spatial_pos_bf16) cudaFree(h->d_spatial_pos_bf16);
   if (h->d_temporal_pos) cudaFree(h->d_temporal_pos);
   if (h->d_pe) cudaFree(h->d_pe);
   if (h->pipe_init) {

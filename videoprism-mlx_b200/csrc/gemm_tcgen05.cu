@@ -74,6 +74,7 @@ struct KParams {
   int pos_period;
   const bf16* resid;
   int ldr;
+  int resid_period;   // > 0: residual rows repeat with this period (a table), see GemmEpilogue
   const float* ln_stats_in;
   int ln_slots;
   const float* ln_colsum;
@@ -291,14 +292,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int mrow0 = m0 + q * 32;
       const int ncol0 = n0 + slice * CW;
+      const int rrow0 = (RESID && p.resid_period > 0) ? mrow0 % p.resid_period : mrow0;   // first row of the residual tile
       if (!OUT_F32 && leader) {
         tma_store_wait_read<0>();   // the previous tile's last store has finished reading the staging tile
         if (RESID) {
           mbar_expect_tx(resid_bar(e, 0), C::kStageTileBytes);
-          tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, mrow0);
+          tma_load_2d(stg, &tmR, resid_bar(e, 0), ncol0, rrow0);
           if (two_bufs && NCH > 1) {
             mbar_expect_tx(resid_bar(e, 1), C::kStageTileBytes);
-            tma_load_2d(stg + C::kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, mrow0);
+            tma_load_2d(stg + C::kStageTileBytes, &tmR, resid_bar(e, 1), ncol0 + 32, rrow0);
           }
         }
       }
@@ -384,7 +386,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 upk2(v[2 * g], a, b);
                 upk2(v[2 * g + 1], c, d);
                 if (RESID) {
-                  const uint2 rr = *reinterpret_cast<const uint2*>(p.resid + static_cast<size_t>(m) * p.ldr + n + g * 4);
+                  const uint2 rr = *reinterpret_cast<const uint2*>(p.resid + static_cast<size_t>(rrow0 + lane) * p.ldr + n + g * 4);
                   a += bf16_lo(rr.x); b += bf16_hi(rr.x); c += bf16_lo(rr.y); d += bf16_hi(rr.y);
                 }
                 *reinterpret_cast<float4*>(cp + g * 4) = make_float4(a, b, c, d);
@@ -440,7 +442,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (RESID && !two_bufs && ch + 1 < NCH) {
               tma_store_wait_read<0>();
               mbar_expect_tx(resid_bar(e, 0), C::kStageTileBytes);
-              tma_load_2d(stg, &tmR, resid_bar(e, 0), n + 32, mrow0);
+              tma_load_2d(stg, &tmR, resid_bar(e, 0), n + 32, rrow0);
             }
           }
           __syncwarp();
@@ -602,8 +604,9 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   } else {
     m.c = m.a;
   }
+  if (epi.resid_period < 0 || (epi.resid_period % 32) != 0) return cudaErrorInvalidValue;
   if (epi.resid != nullptr && !epi.out_f32) {
-    if (!make_tmap_2d_bf16(&m.r, epi.resid, M, N, epi.ldr, 32, 32, 64)) return cudaErrorUnknown;
+    if (!make_tmap_2d_bf16(&m.r, epi.resid, epi.resid_period > 0 ? epi.resid_period : M, N, epi.ldr, 32, 32, 64)) return cudaErrorUnknown;
   } else {
     m.r = m.a;
   }
@@ -614,7 +617,7 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   kp.row_scale = epi.row_scale;
   kp.pos_table = epi.pos_table;
   kp.pos_period = epi.pos_period > 0 ? epi.pos_period : 1;
-  kp.resid = epi.resid; kp.ldr = epi.ldr;
+  kp.resid = epi.resid; kp.ldr = epi.ldr; kp.resid_period = epi.resid != nullptr ? epi.resid_period : 0;
   kp.ln_stats_in = epi.ln_stats_in; kp.ln_colsum = epi.ln_colsum; kp.ln_slots = epi.ln_slots > 0 ? epi.ln_slots : 1;
   kp.stats_slots = gemm_stats_slots(N);
   kp.ln_inv_dim = epi.ln_dim > 0 ? 1.0f / static_cast<float>(epi.ln_dim) : 0.f;

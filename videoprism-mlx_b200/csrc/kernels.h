@@ -21,6 +21,8 @@ struct GemmEpilogue {
   int pos_period = 0;
   const bf16* resid = nullptr;       // [M, ldr] bf16 residual stream (layers.py:855, :425); may alias C
   int ldr = 0;
+  int resid_period = 0;              // > 0: resid is a [resid_period, ldr] table indexed by (m % resid_period), resid_period % 32 == 0
+                                     // (the spatial position table in bf16: the patch projection's `+ emb_var`, encoders.py:514)
   int out_f32 = 0;                   // C is float* when set
   // LayerNorm folded into the GEMM (layers.py:237-270 applied to the A rows):  A holds the RAW rows x, Wt holds
   // (gamma1 (.) W)^T, and   v = rstd[m] * acc - rstd[m] * mean[m] * ln_colsum[n] + bias[n]   with bias = beta.W + b.
