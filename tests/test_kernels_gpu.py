@@ -100,6 +100,20 @@ def test_gemm_epilogues(L, act):
     _close(run_gemm(L, A, Wt, bias, act=act, pos=pos), ref_gemm(A, Wt, bias, act=act, pos=pos))
 
 
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_epilogues_on_the_sm_pair_path(L, act):
+    """Same epilogues at a size that runs on SM pairs (cta_group::2, 256 x 256 tiles), with a ragged last M tile."""
+    g = torch.Generator(device="cuda").manual_seed(10 + act)
+    M, N, K = 16640 + 19, 768, 256
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    Wt = (torch.randn((N, K), device="cuda", generator=g) * 0.1).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    resid = torch.randn((M, N), device="cuda", generator=g).bfloat16()
+    rs = (torch.rand((M,), device="cuda", generator=g) > 0.3).float()
+    _close(run_gemm(L, A, Wt, bias, act=act), ref_gemm(A, Wt, bias, act=act))
+    _close(run_gemm(L, A, Wt, bias, act=act, resid=resid, row_scale=rs), ref_gemm(A, Wt, bias, act=act, resid=resid, row_scale=rs))
+
+
 def test_gelu_epilogue_accuracy(L):
     """The epilogue's GELU (tanh form with a fitted inner polynomial + MUFU.TANH) against exact erf GELU
     (layers.py:31) over every bf16 input in [-12, 12]: feed x through a rank-1 product so acc == x exactly."""

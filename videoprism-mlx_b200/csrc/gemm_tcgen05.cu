@@ -83,6 +83,7 @@ struct KParams {
   int stats_slots;
   int stages;   // smem ring depth (Cfg::stages)
   int nbuf;     // staging tiles per epilogue warp (1 or 2)
+  int cl;       // CTAs per cluster: CG, or 4 = two SM pairs on M-adjacent tiles that share (TMA-multicast) their B tile
 };
 
 template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
@@ -113,13 +114,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   constexpr int TM = BM * CG;                                  // rows of one (pair) tile
-  const int num_m_tiles = (p.M + TM - 1) / TM;
+  // A cluster holds npairs SM pairs (1, or 2 with p.cl == 4) that work on M-adjacent tiles of the same N tile, so
+  // they read the same B (weight) tile: each CTA fetches half of its B share and multicasts it to its twin in the other
+  // pair.  A "tile" below is the cluster's unit: npairs x TM rows by BN columns.
+  const int crank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cta_rank = crank & 1;                              // rank inside the MMA pair
+  const int pi = crank >> 1;                                   // which pair of the cluster
+  const int npairs = (CG == 2) ? p.cl / 2 : 1;
+  const int num_m_tiles = ((p.M + TM - 1) / TM + npairs - 1) / npairs;
   const int num_n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
-  const int tile0 = static_cast<int>(blockIdx.x) / CG;         // first tile of this CTA (pair)
-  const int tile_step = static_cast<int>(gridDim.x) / CG;
+  const int tile0 = static_cast<int>(blockIdx.x) / ((CG == 2) ? p.cl : 1);         // first tile of this cluster
+  const int tile_step = static_cast<int>(gridDim.x) / ((CG == 2) ? p.cl : 1);
+  auto tile_m0 = [&](int tile) { return ((tile / num_n_tiles) * npairs + pi) * TM + cta_rank * BM; };   // this CTA's 128 A rows
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -130,7 +138,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), npairs);   // every pair of the cluster must have consumed the slot (B is multicast into it)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -164,13 +172,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;            // this CTA's 128 A rows
+        const int m0 = tile_m0(tile);
         const int n0 = (tile % num_n_tiles) * BN + cta_rank * C::kBRows;     // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + C::kABytes;
-          if (CG == 2) {
+          if (CG == 2 && npairs == 2) {
+            // Clusters of 4: as for plain pairs the bytes are credited to the pair leader's full barrier; this CTA fetches
+            // half of its B share (64 rows) and multicasts it to itself and its twin (same pair rank, other pair), the
+            // twin supplies the other half.
+            const int hrows = C::kBRows / 2;
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d_pair_mc(sb + pi * hrows * (BK * 2), &tmB, full_bar(stage), kb * BK, n0 + pi * hrows,
+                                static_cast<uint16_t>(5u << cta_rank));
+          } else if (CG == 2) {
             // both CTAs' bytes are credited to the leader's full barrier; only the leader arms it
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
             tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BK, m0);
@@ -211,10 +228,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (CG == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+          if (CG == 2) umma_commit_pair(empty_bar(stage), static_cast<uint16_t>(npairs == 2 ? 0xF : 0x3)); else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if (CG == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));  // accumulator complete
+        if (CG == 2) umma_commit_pair(tfull_bar(acc), static_cast<uint16_t>(0x3 << (2 * pi))); else umma_commit(tfull_bar(acc));  // accumulator complete
       }
     }
   } else if (warp == 2 || warp == 3) {
@@ -226,7 +243,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ht = static_cast<int>(threadIdx.x) - 64;   // 0..63
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-      const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;
+      const int m0 = tile_m0(tile);
       const int n0 = (tile % num_n_tiles) * BN;
       float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
       const int n = n0 + ht * 4;
@@ -286,7 +303,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t rphase = 0;
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-      const int m0 = (tile / num_n_tiles) * TM + cta_rank * BM;
+      const int m0 = tile_m0(tile);
       const int n0 = (tile % num_n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
@@ -333,7 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+            if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 2 * pi); else mbar_arrive(tempty_bar(acc));
           }
         }
         const int n = n0 + col;
@@ -528,6 +545,7 @@ template <int BN, int ACT, bool RESID, bool OUT_F32, int CG>
 cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp_in, int grid) {
   auto kern = gemm_bf16_kernel<BN, ACT, RESID, OUT_F32, CG>;
   KParams kp = kp_in;
+  if (CG != 2) kp.cl = 1;
   // A second staging tile per warp (all residual tiles of a tile requested at its start, one pipeline stage less) was
   // measured neutral for the out-projection (178 vs 175 us in situ): off unless VP_GEMM_NBUF=2.
   static const int nbuf_env = getenv("VP_GEMM_NBUF") ? atoi(getenv("VP_GEMM_NBUF")) : 1;
@@ -549,8 +567,19 @@ cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp_in, i
   int na = 0;
   if (CG == 2) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    attr[na].val.clusterDim.x = kp.cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
+    if (kp.cl == 4) {
+      // clusters of four 227 KB CTAs do not tile all 148 SMs (GPCs of 16 / 18 / 20 SMs): ask how many fit
+      static int max_clusters = 0;
+      if (max_clusters == 0) {
+        cfg.attrs = attr; cfg.numAttrs = na;
+        cfg.gridDim = dim3(4 * 37);
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = 32;
+      }
+      const int want = grid / 4;
+      cfg.gridDim = dim3(4 * (want < max_clusters ? want : max_clusters));
+    }
   }
   if (pdl_enabled()) {   // programmatic dependent launch: the prologue overlaps the previous kernel's tail (ptx.cuh: pdl_wait)
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -596,9 +625,14 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   int CG = (BN == 256 && !epi.out_f32 && pair_tiles >= num_sms() / 2) ? 2 : 1;
   if (force_cg == 1) CG = 1;
   if (force_cg == 2 && BN == 256) CG = 2;
+  // Clusters of 4 (two SM pairs on M-adjacent tiles sharing one TMA-multicast B tile: 25 % fewer L2 reads) are
+  // implemented but OFF: only 33 such clusters fit (132 of 148 SMs) and the forward measured 1077 vs 1050-1083 clips/s,
+  // i.e. the power the main loop spends on operand delivery is not in the L2 read that multicast saves.
+  static const int cluster_env = getenv("VP_GEMM_CLUSTER") ? atoi(getenv("VP_GEMM_CLUSTER")) : 2;
+  const int cl = (CG == 2 && cluster_env == 4 && pair_tiles >= num_sms()) ? 4 : CG;
   Maps m;
   if (!make_tmap_2d_bf16(&m.a, A, M, K, lda, BM, BK, 128)) return cudaErrorUnknown;
-  if (!make_tmap_2d_bf16(&m.b, Wt, N, K, ldb, BN / CG, BK, 128)) return cudaErrorUnknown;
+  if (!make_tmap_2d_bf16(&m.b, Wt, N, K, ldb, cl == 4 ? BN / 4 : BN / CG, BK, 128)) return cudaErrorUnknown;
   if (!epi.out_f32) {
     if (!make_tmap_2d_bf16(&m.c, Cout, M, N, ldc, 32, 32, 64)) return cudaErrorUnknown;
   } else {
@@ -624,7 +658,12 @@ cudaError_t launch_gemm(cudaStream_t s, const bf16* A, int lda, const bf16* Wt, 
   kp.stats_out = epi.stats_out;
   if (epi.ln_stats_in != nullptr && (epi.ln_colsum == nullptr || epi.ln_dim <= 0)) return cudaErrorInvalidValue;
   if (epi.stats_out != nullptr && epi.out_f32) return cudaErrorInvalidValue;
+  kp.cl = cl;
   if (CG == 2) {
+    if (cl == 4) {   // grid in CTAs; launch_gemm_t clamps it to the number of clusters that fit
+      const int cluster_tiles = (((M + 255) / 256 + 1) / 2) * (N / 256);
+      return launch_gemm_bn<256, 2>(s, m, kp, 4 * cluster_tiles, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
+    }
     const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
     return launch_gemm_bn<256, 2>(s, m, kp, 2 * pairs, epi.act, epi.resid != nullptr, epi.out_f32 != 0);
   }

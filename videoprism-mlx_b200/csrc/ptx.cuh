@@ -206,6 +206,14 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtens
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+// cta_group::2 TMA load multicast to the CTAs of `cta_mask` (cluster ranks): the box lands at the same smem offset in every
+// destination CTA; the bytes are credited to the full barrier of each destination CTA's PAIR LEADER (peer bit cleared).
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -226,9 +234,9 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_de
       : "memory");
 }
 // commit: arrive (once) on the mbarrier at this smem offset in BOTH CTAs when the pair's MMAs retire
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(static_cast<uint16_t>(3))
+               ::"r"(bar), "h"(cta_mask)
                : "memory");
 }
 
