@@ -1,21 +1,22 @@
 // bf16 GEMM for sm_100a: C[M,N] = A[M,K] * Wt[N,K]^T with a fused epilogue.
 //
-// Persistent, warp-specialised:
+// Persistent, warp-specialised (640 threads):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles)
-//   warp 1      : MMA issuer    (one elected thread, tcgen05.mma kind::f16, M=128 x N=BN x K=16)
-//   warp 2      : TMEM allocator
+//   warp 1      : MMA issuer    (one elected thread, tcgen05.mma kind::f16; on SM pairs cta_group::2, M=256 x N=256 x K=16)
+//   warps 2, 3  : TMEM allocator (warp 2) and "stagers": per-column {colsum, bias} and, for a folded LayerNorm, the
+//                 per-row (rstd, -rstd*mean) of the NEXT tile -> shared memory
 //   warps 4..19 : epilogue      (tcgen05.ld -> folded LayerNorm / bias / GELU / row-scale / pos-emb / residual -> bf16)
 // The fp32 accumulator lives in TMEM and is double buffered (2 x BN columns), so the epilogue of
-// tile i overlaps the main loop of tile i+1.  The smem ring has kStages slots of (128 x 64 A,
-// BN x 64 B) bf16.
+// tile i overlaps the main loop of tile i+1.  The smem ring has 5-6 slots of (128 x 64 A, BN/CG x 64 B) bf16.
 //
 // The epilogue is latency-, not throughput-bound (ncu: 2 epilogue warps per scheduler issued 0.19 IPC each and
 // made the K=768 GEMMs epilogue-bound), so it runs 16 warps (4 per scheduler), each owning 32 accumulator rows x
-// BN/4 columns, and fetches everything but the accumulator before it waits for the MMA: per-column constants go
-// to shared memory once per tile and are read back as broadcast 16-byte loads, the bf16 residual tile is
-// TMA-loaded into the warp's staging tile.  Data movement is all TMA: the converted 32 x BN/4 tile is written to
-// the swizzled (conflict-free) staging tile and stored with ONE cp.async.bulk.tensor per warp and tile.
-// (Row-per-thread global stores cost 32 L1 wavefronts per instruction.)
+// BN/4 columns, and everything but the accumulator is fetched before the MMA completes: the stagers' vectors are
+// read back as broadcast 16-byte shared loads, the bf16 residual tile is TMA-loaded into the warp's staging tile.
+// Data movement is all TMA: each converted 32 x 32 chunk goes through the warp's swizzled (conflict-free) staging
+// tile and out with one cp.async.bulk.tensor.  (Row-per-thread global stores cost 32 L1 wavefronts per instruction.)
+// Every single-lane issue site is predicated with elect.sync, not `lane == 0`: ptxas otherwise wraps each
+// UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop (11 instructions per MMA instead of 4).
 //
 // Replaces the reference's nn.Dense / einsum projections (layers.py:304-312, :486-488, :483-498).
 #include <cuda.h>
@@ -50,7 +51,7 @@ struct Cfg {
   static constexpr int staging_bytes(int nbuf) { return kNumEpiWarps * nbuf * kStageTileBytes; }
   static constexpr int kCvecBytes = BN * 8;                   // {colsum[n], colsum[n+1], bias[n], bias[n+1]} per column pair
   static constexpr int kRowvecBytes = BM * 8;                 // folded LayerNorm: (rstd, -rstd * mean) per accumulator row
-  static constexpr int kBarBytes = 512;                       // (2*stages + 4 + 16 + 2) mbarriers + the TMEM base pointer
+  static constexpr int kBarBytes = 512;                       // (2*stages + 4 + 2*16 + 2) mbarriers + the TMEM base pointer
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
   // The main loop needs ~150 KB of loads in flight per SM (64 B/clk at ~1.5 us of L2/HBM latency), so everything
   // else is kept small and the rest of the 227 KB is pipeline: 6 stages of 32 KB for SM pairs (5 when the folded
