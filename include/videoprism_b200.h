@@ -131,6 +131,14 @@ VP_API int vp_device_sm_count(void);                    /* < 0 when no CUDA devi
 VP_API int vp_trace(vp_handle* h, int enable);
 VP_API int vp_trace_report(vp_handle* h, char* buf, int cap);
 
+/* -- frame ingest (videoprism/video_utils.py:20-94 load_video, :97-127 _center_crop_resize), device memory:
+ *    decoded RGB uint8 frames [T, H, W, 3] of any size -> uint8 [T, target_size, target_size, 3], bit-exact with the
+ *    cv2.resize (INTER_LINEAR, fixed point) + centre crop the reference performs on the host.  resize_mode 0 =
+ *    "center_crop" (shortest side -> target_size, then crop), 1 = "resize" (may distort).  The result feeds
+ *    vp_encoder_forward_u8, which applies the /255 of video_utils.py:91. */
+VP_API int vp_resize_frames_u8(const uint8_t* frames, int T, int H, int W, uint8_t* out, int target_size, int resize_mode,
+                        void* stream);
+
 /* -- kernel-level entry points (device pointers; used by the parity tests and micro-benchmarks) ---
  *    C[M,N] = A[M,K] * Wt[N,K]^T (+bias[N]) ; act 0 none, 1 exact GELU, 2 ReLU ; optional bf16 residual. */
 VP_API int vp_gemm_bf16(const void* A, int lda, const void* Wt, int ldb, void* C, int ldc, int M, int N, int K,

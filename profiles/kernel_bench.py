@@ -144,3 +144,11 @@ if model == "base":
     print(f"attention auxiliary S=4096 (tcgen05 key loop), {max(B // 8, 1)} clips: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
     ms, tf = attention(B // 8 if B >= 8 else 1, T * N, 1, force=1)
     print(f"attention auxiliary S=4096 (mma.sync flash), {max(B // 8, 1)} clips: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s")
+# frame ingest: 8 clips of 16 frames, 640x360 -> 288x288 centre crop (HBM-bound: source window read once + output)
+fr = torch.randint(0, 256, (8 * 16, 360, 640, 3), dtype=torch.uint8, device="cuda")
+dst = torch.empty((8 * 16, 288, 288, 3), dtype=torch.uint8, device="cuda")
+def f_ingest():
+    assert lib.vp_resize_frames_u8(fr.data_ptr(), 8 * 16, 360, 640, dst.data_ptr(), 288, 0, st) == 0
+ms = timeit(f_ingest)
+algo = 8 * 16 * (360 * 450 * 3 + 288 * 288 * 3)   # the cropped source window (360 x 450) + the output
+print(f"frame ingest 8x16x360x640 -> 288^2: {ms*1e3:8.1f} us  {algo / ms / 1e6:7.0f} GB/s algorithmic")

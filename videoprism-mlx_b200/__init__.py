@@ -6,6 +6,7 @@ There is no CPU fallback: importing is cheap, but creating a model without the b
 without a B200 raises.
 """
 from . import models  # noqa: F401
+from . import video_utils  # noqa: F401
 from .models import (  # noqa: F401
     CONFIGS, MODELS, get_model, has_model, load_pretrained_weights, load_video_encoder, load_model,
     FactorizedEncoder, FactorizedVideoCLIP, synthetic_state, pinned_empty, compute_similarity_matrix,

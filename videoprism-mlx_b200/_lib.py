@@ -55,6 +55,7 @@ _PROTOS = {
     "vp_fold_ln_weight": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.c_float, _P]),
     "vp_layernorm": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vp_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "vp_resize_frames_u8": (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
     "vp_attention": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.c_float, _P, _I, _P]),
 }
 

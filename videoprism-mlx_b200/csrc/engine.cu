@@ -1106,6 +1106,11 @@ int vp_patchify(const float* video, void* out, int ldo, int BT, int H, int W, in
   return ck(vp::launch_patchify(static_cast<cudaStream_t>(stream), video, static_cast<bf16*>(out), ldo, BT, H, W, p));
 }
 
+int vp_resize_frames_u8(const uint8_t* frames, int T, int H, int W, uint8_t* out, int target_size, int resize_mode, void* stream) {
+  if (frames == nullptr || out == nullptr) return VP_ERR_INVALID;
+  return ck(vp::launch_resize_frames_u8(static_cast<cudaStream_t>(stream), frames, T, H, W, out, target_size, resize_mode));
+}
+
 int vp_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int num_seq, int S, int group,
                  int heads, int dh, float cap, const float* key_pad, int causal, void* stream) {
   vp::AttnArgs a;

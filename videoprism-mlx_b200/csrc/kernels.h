@@ -64,6 +64,10 @@ cudaError_t launch_patchify(cudaStream_t s, const float* video, bf16* out, int l
 // same for uint8 frames: value / 255.0f in fp32 first, exactly as video_utils.load_video does (video_utils.py:88-93)
 cudaError_t launch_patchify_u8(cudaStream_t s, const uint8_t* video, bf16* out, int ldo, int BT, int H, int W, int p);
 
+// Frame ingest (video_utils.py:74-84, :97-127): uint8 RGB [T, H, W, 3] -> uint8 [T, target, target, 3], bit-exact with
+// cv2.resize (INTER_LINEAR) + the reference's centre crop.  mode 0 = "center_crop", 1 = "resize".
+cudaError_t launch_resize_frames_u8(cudaStream_t s, const uint8_t* src, int T, int H, int W, uint8_t* dst, int target, int mode);
+
 // Attention over sequences embedded in a packed qkv buffer [rows, ld] (q at col q_off + h*dh, ...).
 // Sequence `sid` token j lives at row (sid / group) * (group * S) + (sid % group) + j * group.
 //   spatial stack : group = 1           (tokens of a frame are contiguous)
