@@ -42,7 +42,8 @@ typedef enum vp_dtype { VP_F32 = 0, VP_BF16 = 1, VP_I32 = 2, VP_U8 = 3 } vp_dtyp
 
 typedef enum vp_model_kind {
   VP_KIND_ENCODER = 0, /* encoders.FactorizedEncoder   (videoprism/encoders.py:391-580) */
-  VP_KIND_CLIP = 1     /* encoders.FactorizedVideoCLIP (videoprism/encoders.py:762-910) */
+  VP_KIND_CLIP = 1,    /* encoders.FactorizedVideoCLIP (videoprism/encoders.py:762-910) */
+  VP_KIND_CLASSIFIER = 2 /* encoders.FactorizedVideoClassifier (videoprism/encoders.py:583-653) */
 } vp_model_kind;
 
 /* Mirrors the CONFIGS dict entries of videoprism/models.py:82-161 (and MODEL_CONFIGS,
@@ -60,6 +61,7 @@ typedef struct vp_config {
   int num_auxiliary_layers; /* CLIP only */
   int num_unimodal_layers;  /* CLIP only */
   int vocabulary_size;      /* CLIP only */
+  int num_classes;          /* classifier only (videoprism/models.py:200-221) */
 } vp_config;
 
 /* -- lifecycle: replaces models.get_model (videoprism/models.py:268-303) and
@@ -116,6 +118,14 @@ VP_API int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, i
                                float* video_emb, void* stream);
 VP_API int vp_clip_text_forward_host(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
                               float* text_emb, void* stream);
+
+/* -- FactorizedVideoClassifier.__call__ (videoprism/encoders.py:596-653; models_mlx.load_classifier,
+ *    videoprism/models_mlx.py:213-294): encoder -> atten_pooler (hidden_dim = model_dim) -> projection.
+ *    logits [B, num_classes] fp32.  Optional outputs (NULL to skip), fp32: global_embeddings [B,D],
+ *    spatial_features / spatiotemporal_features [B,T*N,D].  Device memory throughout. */
+VP_API int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
+                          float* logits, float* global_embeddings, float* spatial_features, float* spatiotemporal_features,
+                          void* stream);
 
 /* -- retrieval similarity (README.md:81; colab compute_similarity_matrix): sim[i,j] = v[i] . t[j].
  *    v [Nv,D], t [Nt,D], sim [Nv,Nt], fp32 device memory. */

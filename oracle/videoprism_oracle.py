@@ -61,6 +61,8 @@ def tiny_config(kind: str = "encoder", **over) -> dict:
                atten_logit_cap=50.0)
     if kind == "clip":
         cfg.update(num_auxiliary_layers=1, num_unimodal_layers=2, vocabulary_size=128)
+    if kind == "classifier":
+        cfg.update(num_classes=10)
     cfg.update(over)
     return cfg
 
@@ -113,17 +115,9 @@ def _encoder_specs(prefix: str, cfg: dict) -> List[Tuple[str, tuple, str]]:
     return s
 
 
-def param_specs(cfg: dict) -> List[Tuple[str, tuple, str]]:
-    """Ordered (flax_key, shape, kind) list for a config."""
-    if cfg["kind"] == "encoder":
-        return _encoder_specs("params", cfg)
-    D, H, F = cfg["model_dim"], cfg["num_heads"], cfg["mlp_dim"]
-    s = _encoder_specs("params/vision_encoder", cfg)
-    if cfg["num_auxiliary_layers"] > 0:
-        s += _stack_specs("params/auxiliary_encoder/transformers_stack", cfg["num_auxiliary_layers"], D, H, F)
-    ph = 4 * D // H  # pooler: hidden_dim = 4*D (encoders.py:861), dim_per_head = hidden/H (layers.py:708-713)
-    pp = "params/contrastive_vision_pooler"
-    s += [
+def _pooler_specs(pp: str, D: int, H: int, ph: int) -> List[Tuple[str, tuple, str]]:
+    """AttenTokenPoolingLayer leaves (layers.py:1044-1136; 12 leaves, layers_test.py:282)."""
+    return [
         (pp + "/pooling_attention_query", (1, D), "matrix"),
         (pp + "/pooling_attention/query/w", (D, H, ph), "matrix"),
         (pp + "/pooling_attention/query/b", (H, ph), "bias"),
@@ -137,6 +131,26 @@ def param_specs(cfg: dict) -> List[Tuple[str, tuple, str]]:
         (pp + "/pooling_attention_layer_norm/scale", (D,), "ln_scale"),
         (pp + "/pooling_attention_layer_norm/bias", (D,), "bias"),
     ]
+
+
+def param_specs(cfg: dict) -> List[Tuple[str, tuple, str]]:
+    """Ordered (flax_key, shape, kind) list for a config."""
+    if cfg["kind"] == "encoder":
+        return _encoder_specs("params", cfg)
+    D, H, F = cfg["model_dim"], cfg["num_heads"], cfg["mlp_dim"]
+    if cfg["kind"] == "classifier":
+        # FactorizedVideoClassifier (encoders.py:583-653): encoder, atten_pooler with hidden_dim = model_dim (:631-638,
+        # so dim_per_head = D/H), projection Dense to num_classes (:643-650)
+        s = _encoder_specs("params/encoder", cfg)
+        s += _pooler_specs("params/atten_pooler", D, H, D // H)
+        s += [("params/projection/linear/kernel", (D, cfg["num_classes"]), "matrix"),
+              ("params/projection/linear/bias", (cfg["num_classes"],), "bias")]
+        return s
+    s = _encoder_specs("params/vision_encoder", cfg)
+    if cfg["num_auxiliary_layers"] > 0:
+        s += _stack_specs("params/auxiliary_encoder/transformers_stack", cfg["num_auxiliary_layers"], D, H, F)
+    ph = 4 * D // H  # pooler: hidden_dim = 4*D (encoders.py:861), dim_per_head = hidden/H (layers.py:708-713)
+    s += _pooler_specs("params/contrastive_vision_pooler", D, H, ph)
     tp = "params/text_encoder"
     s += [
         (tp + "/token_emb/emb_var", (cfg["vocabulary_size"], D), "matrix"),
@@ -414,15 +428,15 @@ def _contains(coll, key: str) -> bool:
     return coll if isinstance(coll, bool) else key in coll
 
 
-def atten_token_pool(W: Dict[str, torch.Tensor], tokens: torch.Tensor, n_heads: int) -> torch.Tensor:
-    """AttenTokenPoolingLayer (layers.py:1072-1136): 1 learned query, hidden 4*D,
+def atten_token_pool(W: Dict[str, torch.Tensor], tokens: torch.Tensor, n_heads: int, hidden_dim: Optional[int] = None) -> torch.Tensor:
+    """AttenTokenPoolingLayer (layers.py:1072-1136): 1 learned query, hidden 4*D unless given (:1088),
     PerDimScale on q, no logit cap, LayerNorm after.  tokens [B,S,D] -> [B,1,D]."""
     B, S, D = tokens.shape
     q = W["pooling_attention_query"][None].expand(B, -1, -1)               # :1093-1101
     mask = paddings_to_mask(torch.zeros(B, S, dtype=tokens.dtype))         # :1102-1104
     att = _sub(W, "pooling_attention")
     out = attention_layer(q, tokens, att, mask, 0.0,
-                          per_dim_scale=att["per_dim_scale/per_dim_scale"], hidden_dim=4 * D)
+                          per_dim_scale=att["per_dim_scale/per_dim_scale"], hidden_dim=hidden_dim or 4 * D)
     return layer_norm(out, W["pooling_attention_layer_norm/scale"], W["pooling_attention_layer_norm/bias"])  # :1124-1129
 
 
@@ -489,6 +503,19 @@ def clip_forward(cfg: dict, W: Dict[str, torch.Tensor], video: Optional[torch.Te
     return v_emb, t_emb, outs
 
 
+def classifier_forward(cfg: dict, W: Dict[str, torch.Tensor], video: torch.Tensor,
+                       return_intermediate: bool | Collection[str] = False, frame_paddings: Optional[torch.Tensor] = None):
+    """FactorizedVideoClassifier.__call__ (encoders.py:596-653)."""
+    f, outs = encoder_forward(cfg, W, video, return_intermediate, frame_paddings, prefix="params/encoder")    # :616-627
+    if _contains(return_intermediate, "spatiotemporal_features"):                                           # :628-629
+        outs["spatiotemporal_features"] = f
+    emb = atten_token_pool(_sub(W, "params/atten_pooler"), f, cfg["num_heads"], hidden_dim=cfg["model_dim"])[:, 0]  # :631-639
+    if _contains(return_intermediate, "global_embeddings"):                                                 # :641-642
+        outs["global_embeddings"] = emb
+    logits = emb @ W["params/projection/linear/kernel"] + W["params/projection/linear/bias"]                # :643-650
+    return logits, outs
+
+
 # ----------------------------------------------------------------------------
 # Convenience entry points used by tests / bench
 # ----------------------------------------------------------------------------
@@ -510,6 +537,13 @@ def run_clip(cfg: dict, weights: Dict[str, np.ndarray], video=None, ids=None, pa
             None if paddings is None else torch.from_numpy(paddings).to(dtype), **kw)
     return (None if v is None else v.numpy(), None if t is None else t.numpy(),
             {k: o.numpy() for k, o in outs.items()})
+
+
+def run_classifier(cfg: dict, weights: Dict[str, np.ndarray], video: np.ndarray, dtype=torch.float32, **kw):
+    W = to_torch(weights, dtype)
+    with torch.no_grad():
+        logits, outs = classifier_forward(cfg, W, torch.from_numpy(video).to(dtype), **kw)
+    return logits.numpy(), {k: v.numpy() for k, v in outs.items()}
 
 
 def count_params(cfg: dict) -> int:

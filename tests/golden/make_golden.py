@@ -86,6 +86,22 @@ def tiny_cases():
             for k, a in outs.items():
                 arrays[k] = np.asarray(a)
     save("clip_tiny", **arrays)
+    classifier_case()
+
+
+def classifier_case():
+    # encoders_test.py:183-231: tiny FactorizedVideoClassifier (encoder + atten_pooler + projection), all intermediates,
+    # with and without frame paddings
+    cfg = O.tiny_config("classifier")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(3, 4, 16, seed=14, kind="normal")
+    fp = np.zeros((3, 4), np.float32); fp[1, 3:] = 1; fp[2, 1:] = 1
+    enc = {k: x for k, x in cfg.items() if k not in ("kind", "num_classes")}
+    m = encoders.FactorizedVideoClassifier(encoder_params=dict(scan=True, **enc), num_classes=cfg["num_classes"])
+    logits, outs = m.apply(tree_of(W), jnp.asarray(v), train=False, return_intermediate=True)
+    logits_p, _ = m.apply(tree_of(W), jnp.asarray(v), train=False, frame_paddings=jnp.asarray(fp))
+    save("classifier_tiny", logits=np.asarray(logits), logits_frame_paddings=np.asarray(logits_p), frame_paddings=fp,
+         **{k: np.asarray(a) for k, a in outs.items()})
 
 
 def full_size_cases():
@@ -117,6 +133,9 @@ def full_size_cases():
 
 
 if __name__ == "__main__":
+    if "--classifier-only" in sys.argv:
+        classifier_case()
+        sys.exit(0)
     tiny_cases()
     if "--tiny-only" not in sys.argv:
         full_size_cases()

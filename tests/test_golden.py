@@ -53,6 +53,23 @@ def test_tiny_clip():
     assert np.abs(ve - g["video_emb_raw"]).max() <= FEAT_TOL and np.abs(te - g["text_emb_raw"]).max() <= FEAT_TOL
 
 
+def test_tiny_classifier():
+    """encoders_test.py:183-231 shapes: FactorizedVideoClassifier through the reference's own code."""
+    g = load("classifier_tiny")
+    cfg = O.tiny_config("classifier")
+    W = O.make_synthetic_weights(cfg)
+    assert len(W) == 54                                   # encoders_test.py:224
+    v = O.make_video(3, 4, 16, seed=14, kind="normal")
+    logits, outs = O.run_classifier(cfg, W, v, return_intermediate=True)
+    assert logits.shape == (3, 10)
+    assert np.abs(logits - g["logits"]).max() <= FEAT_TOL
+    for k in ("spatial_features", "spatiotemporal_features", "global_embeddings"):
+        assert np.abs(outs[k] - g[k]).max() <= FEAT_TOL
+    lp, _ = O.run_classifier(cfg, W, v, frame_paddings=torch.from_numpy(g["frame_paddings"]))
+    assert np.abs(lp - g["logits_frame_paddings"]).max() <= FEAT_TOL
+    assert np.abs(lp - logits).max() > 1e-3
+
+
 @pytest.mark.parametrize("case,T,seed,kind", [("base_config1", 16, 0, "uniform"), ("base_T8", 8, 1, "normal")])
 def test_base_encoder_full_size(case, T, seed, kind):
     g = load(case)

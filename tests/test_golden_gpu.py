@@ -89,3 +89,28 @@ def test_lvt_base_one_clip_three_queries():
     ve, te, _ = m.apply(W, v, g["ids"], g["paddings"], train=False, normalize=False)
     check("lvt base video_emb (raw)", ve, g["video_emb_raw"])
     check("lvt base text_emb (raw)", te, g["text_emb_raw"])
+
+
+def test_tiny_classifier_case():
+    """FactorizedVideoClassifier (encoders.py:583-653) against the reference-generated golden: logits within 2e-2 absolute
+    (bf16 path; logits are O(0.1), so cosine over 10 classes is also asserted), intermediates by cosine."""
+    import videoprism_b200 as vp
+    g = np.load(os.path.join(G, "classifier_tiny.npz"))
+    cfg = O.tiny_config("classifier")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(3, 4, 16, seed=14, kind="normal")
+    enc = {k: x for k, x in cfg.items() if k not in ("kind", "num_classes")}
+    m = vp.FactorizedVideoClassifier(encoder_params=enc, num_classes=cfg["num_classes"])
+    assert len(m.param_shapes()) == 54                     # encoders_test.py:224
+    logits, outs = m.apply(W, v, train=False, return_intermediate=True)
+    assert logits.shape == (3, 10)
+    for k in ("spatial_features", "spatiotemporal_features", "global_embeddings"):
+        check("classifier " + k, outs[k], g[k])
+    print(f"[golden] classifier logits max-abs {np.abs(logits - g['logits']).max():.4g} (ref max {np.abs(g['logits']).max():.4g})")
+    assert np.abs(logits - g["logits"]).max() <= 2e-2
+    lp, _ = m.apply(W, v, train=False, frame_paddings=g["frame_paddings"])
+    assert np.abs(lp - g["logits_frame_paddings"]).max() <= 2e-2
+    # torch CUDA tensors in -> torch tensors out, same numbers
+    import torch
+    lt, _ = m(torch.from_numpy(v).cuda())
+    assert np.array_equal(lt.cpu().numpy(), logits)

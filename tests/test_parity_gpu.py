@@ -238,3 +238,43 @@ def test_trace_accounts_for_every_launch_and_leaves_results_unchanged():
                  ("temporal.ffn2", 4), ("spatial_ln", 1), ("temporal_ln", 1)):
         assert labels[k][1] == n and labels[k][2] > 0.0
     assert torch.equal(plain, traced)
+
+
+def test_base_classifier_parity():
+    """videoprism_vc_v1_base (models.py:200-205; encoders.py:583-653) at full size, K400 head: one 16x288x288 clip against
+    the fp32 oracle.  Logits are a 768-term dot product of an O(1) LayerNorm output with N(0, 0.02) weights (|logit| ~ 0.5):
+    the bf16 path is held to 3e-2 absolute and cosine >= 0.999 over the class axis; global_embeddings to the token bar."""
+    import videoprism_b200 as vp
+    cfg = dict(O.CONFIGS["videoprism_public_v1_base"], kind="classifier", num_classes=400)
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(1, 16, 288, seed=5)
+    want, wouts = O.run_classifier(cfg, W, v, return_intermediate=("global_embeddings",))
+    m = vp.models.videoprism_vc_v1_base(num_classes=400)
+    got, gouts = m.apply(W, v, train=False, return_intermediate=("global_embeddings",))
+    assert got.shape == (1, 400) and set(gouts) == {"global_embeddings"}
+    c, err = report("base classifier logits", got, want)
+    assert c >= COS_MIN and err <= 3e-2
+    c2, _ = report("  global_embeddings", gouts["global_embeddings"], wouts["global_embeddings"])
+    assert c2 >= COS_MIN
+
+
+def test_load_classifier_takes_the_encoder_of_a_video_text_checkpoint(tmp_path):
+    """models_mlx.load_classifier (models_mlx.py:213-294): `vision_encoder.*` of a video-text checkpoint becomes `encoder.*`,
+    pooler and head are initialised fresh, so spatiotemporal_features equal the video-text model's bit for bit."""
+    import videoprism_b200 as vp
+    cfg = O.tiny_config("clip")
+    W = O.make_synthetic_weights(cfg)
+    path = str(tmp_path / "tiny_lvt.npz")
+    np.savez(path, **W)
+    v = O.make_video(2, 4, 16, seed=6, kind="normal")
+    clip = make_model(cfg)
+    _, _, couts = clip.apply(W, v, None, None, train=False, return_intermediate=("spatiotemporal_features",))
+    models = dict(vp.MODELS)
+    try:
+        vp.MODELS["tiny_lvt"] = lambda: make_model(cfg)
+        m = vp.load_classifier("tiny_lvt", num_classes=5, weights_path=path)
+    finally:
+        vp.MODELS.clear(); vp.MODELS.update(models)
+    logits, outs = m(v, return_intermediate=True)
+    assert logits.shape == (2, 5) and np.isfinite(logits).all()
+    assert np.array_equal(outs["spatiotemporal_features"], couts["spatiotemporal_features"])

@@ -7,9 +7,11 @@ without a B200 raises.
 """
 from . import models  # noqa: F401
 from . import video_utils  # noqa: F401
+from . import tokenizers  # noqa: F401
+from . import utils  # noqa: F401
 from .models import (  # noqa: F401
     CONFIGS, MODELS, get_model, has_model, load_pretrained_weights, load_video_encoder, load_model,
-    FactorizedEncoder, FactorizedVideoCLIP, synthetic_state, pinned_empty, compute_similarity_matrix,
+    FactorizedEncoder, FactorizedVideoCLIP, FactorizedVideoClassifier, load_classifier, get_model_config, synthetic_state, pinned_empty, load_text_tokenizer, tokenize_texts, compute_similarity_matrix,
 )
 
 __version__ = "0.1.0"

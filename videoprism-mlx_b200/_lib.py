@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libvideoprism_b200.so")
 
 VP_OK, VP_ERR_INVALID, VP_ERR_KEY, VP_ERR_INCOMPLETE, VP_ERR_CUDA, VP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 VP_F32, VP_BF16, VP_I32, VP_U8 = 0, 1, 2, 3
-VP_KIND_ENCODER, VP_KIND_CLIP = 0, 1
+VP_KIND_ENCODER, VP_KIND_CLIP, VP_KIND_CLASSIFIER = 0, 1, 2
 
 
 class VpConfig(C.Structure):
@@ -19,6 +19,7 @@ class VpConfig(C.Structure):
         ("model_dim", C.c_int), ("num_spatial_layers", C.c_int), ("num_temporal_layers", C.c_int),
         ("num_heads", C.c_int), ("mlp_dim", C.c_int), ("atten_logit_cap", C.c_float),
         ("num_auxiliary_layers", C.c_int), ("num_unimodal_layers", C.c_int), ("vocabulary_size", C.c_int),
+        ("num_classes", C.c_int),
     ]
 
 
@@ -42,6 +43,7 @@ _PROTOS = {
     "vp_clip_text_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "vp_clip_video_forward_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "vp_clip_text_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "vp_classifier_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "vp_similarity": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vp_workspace_bytes": (C.c_size_t, [_P, _I, _I, _I, _I]),
     "vp_kernel_launches": (C.c_int64, [_P]),

@@ -111,6 +111,9 @@ struct vp_handle {
   std::vector<float> h_pool_query, h_pool_wq, h_pool_bq, h_pool_wk, h_pool_pds;
   float* pool_wkq = nullptr; bf16* pool_wv = nullptr; float* pool_bv = nullptr; bf16* pool_wpost = nullptr;
   float *pool_bpost = nullptr, *pool_ln_g = nullptr, *pool_ln_b = nullptr;
+  int pool_ph = 0;                     // pooler dim_per_head: 4*D/H for the video-text pooler, D/H for the classifier's
+  // classifier head (FactorizedVideoClassifier, encoders.py:643-650)
+  float *cls_w = nullptr, *cls_b = nullptr;
   // text
   float* tok_emb = nullptr; float* cls_emb = nullptr; float* d_pe = nullptr; int pe_len = 0;
   float *uni_ln_g = nullptr, *uni_ln_b = nullptr;
@@ -302,16 +305,12 @@ cudaError_t add_encoder(vp_handle* h, const std::string& prefix) {
   return cudaSuccess;
 }
 
-cudaError_t add_clip_extras(vp_handle* h) {
-  const vp_config& c = h->cfg;
-  const int D = c.model_dim, H = c.num_heads;
-  const int ph = 4 * D / H;  // pooler dim_per_head: hidden 4*D over H heads (encoders.py:861, layers.py:708-713)
+// AttenTokenPoolingLayer parameters (layers.py:1044-1136) under `pp`; ph = hidden_dim / num_heads.
+cudaError_t add_pooler(vp_handle* h, const std::string& pp, int ph) {
+  const int D = h->cfg.model_dim, H = h->cfg.num_heads;
+  h->pool_ph = ph;
   cudaError_t e;
-  if (c.num_auxiliary_layers > 0) {
-    if ((e = add_stack(h, "params/auxiliary_encoder/transformers_stack", &h->aux, c.num_auxiliary_layers, D, H, c.mlp_dim)) != cudaSuccess) return e;
-  }
   vp_handle* hh = h;
-  const std::string pp = "params/contrastive_vision_pooler";
   if ((e = dev_alloc(h, &h->pool_wkq, (size_t)H * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &h->pool_wv, (size_t)H * ph * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &h->pool_bv, (size_t)H * ph)) != cudaSuccess) return e;
@@ -331,6 +330,19 @@ cudaError_t add_clip_extras(vp_handle* h) {
   add_spec(h, pp + "/pooling_attention/post/b", {D}, [hh, D](const float* s, cudaStream_t st) { return copy_f32(s, hh->pool_bpost, D, st); });
   add_spec(h, pp + "/pooling_attention/per_dim_scale/per_dim_scale", {ph}, [hh, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_pds, s, ph, st); });
   if ((e = add_ln(h, pp + "/pooling_attention_layer_norm", &h->pool_ln_g, &h->pool_ln_b, D)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t add_clip_extras(vp_handle* h) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, H = c.num_heads;
+  const int ph = 4 * D / H;  // pooler dim_per_head: hidden 4*D over H heads (encoders.py:861, layers.py:708-713)
+  cudaError_t e;
+  if (c.num_auxiliary_layers > 0) {
+    if ((e = add_stack(h, "params/auxiliary_encoder/transformers_stack", &h->aux, c.num_auxiliary_layers, D, H, c.mlp_dim)) != cudaSuccess) return e;
+  }
+  if ((e = add_pooler(h, "params/contrastive_vision_pooler", ph)) != cudaSuccess) return e;
+  vp_handle* hh = h;
   // text tower (encoders.py:656-759): mlp_dim = 4 * model_dim (:897)
   const std::string tp = "params/text_encoder";
   if ((e = dev_alloc(h, &h->tok_emb, (size_t)c.vocabulary_size * D)) != cudaSuccess) return e;
@@ -426,12 +438,27 @@ int prepare_pos_tables(vp_handle* h, int T, int gh, int gw, cudaStream_t st) {
   return VP_OK;
 }
 
+// FactorizedVideoClassifier (encoders.py:583-653): encoder under 'params/encoder', AttenTokenPoolingLayer 'atten_pooler'
+// with hidden_dim = model_dim (:631-638), FeedForward 'projection' to num_classes (:643-650).
+cudaError_t add_classifier_extras(vp_handle* h) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, NC = c.num_classes;
+  cudaError_t e;
+  if ((e = add_pooler(h, "params/atten_pooler", D / c.num_heads)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->cls_w, (size_t)D * NC)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->cls_b, NC)) != cudaSuccess) return e;
+  vp_handle* hh = h;
+  add_spec(h, "params/projection/linear/kernel", {D, NC}, [hh, D, NC](const float* s, cudaStream_t st) { return copy_f32(s, hh->cls_w, (size_t)D * NC, st); });
+  add_spec(h, "params/projection/linear/bias", {NC}, [hh, NC](const float* s, cudaStream_t st) { return copy_f32(s, hh->cls_b, NC, st); });
+  return cudaSuccess;
+}
+
 // Pooler constants.  The pooling query is a learned parameter, so the projected, PerDimScale'd query
 // qh[h,:] = (query . Wq[:,h,:] + bq[h,:]) * 1.442695041/sqrt(dh) * softplus(pds)   (layers.py:502-527,:1093)
 // is a constant, and scores[s,h] = x[s] . (Wk[:,h,:] qh[h,:]) + const(h): fold to wkq [H, D].
 int finalize_pooler(vp_handle* h) {
   const vp_config& c = h->cfg;
-  const int D = c.model_dim, H = c.num_heads, ph = 4 * D / H;
+  const int D = c.model_dim, H = c.num_heads, ph = h->pool_ph;
   std::vector<double> qh((size_t)H * ph);
   for (int hh = 0; hh < H; ++hh)
     for (int j = 0; j < ph; ++j) {
@@ -646,6 +673,8 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
     g_create_error = "invalid config (model_dim/num_heads/patch_size/mlp_dim)";
     return VP_ERR_INVALID;
   }
+  if (cfg->kind != VP_KIND_ENCODER && cfg->kind != VP_KIND_CLIP && cfg->kind != VP_KIND_CLASSIFIER) { g_create_error = "unknown model kind"; return VP_ERR_INVALID; }
+  if (cfg->kind == VP_KIND_CLASSIFIER && cfg->num_classes <= 0) { g_create_error = "num_classes must be positive for a classifier"; return VP_ERR_INVALID; }
   const int dh = cfg->model_dim / cfg->num_heads;
   if (dh != 64 && dh != 32) { g_create_error = "dim_per_head must be 32 or 64"; return VP_ERR_UNSUPPORTED; }
   int ndev = 0;
@@ -666,8 +695,9 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
     delete h;
     return VP_ERR_UNSUPPORTED;
   }
-  e = add_encoder(h, cfg->kind == VP_KIND_CLIP ? "params/vision_encoder" : "params");
+  e = add_encoder(h, cfg->kind == VP_KIND_CLIP ? "params/vision_encoder" : cfg->kind == VP_KIND_CLASSIFIER ? "params/encoder" : "params");
   if (e == cudaSuccess && cfg->kind == VP_KIND_CLIP) e = add_clip_extras(h);
+  if (e == cudaSuccess && cfg->kind == VP_KIND_CLASSIFIER) e = add_classifier_extras(h);
   if (e != cudaSuccess) {
     g_create_error = std::string("allocation failed: ") + cudaGetErrorString(e);
     vp_destroy(h);
@@ -753,7 +783,7 @@ int vp_finalize(vp_handle* h) {
     int rc = finalize_stack(h, w);
     if (rc != VP_OK) return rc;
   }
-  if (h->cfg.kind == VP_KIND_CLIP) {
+  if (h->cfg.kind == VP_KIND_CLIP || h->cfg.kind == VP_KIND_CLASSIFIER) {
     int rc = finalize_pooler(h);
     if (rc != VP_OK) return rc;
   }
@@ -910,7 +940,7 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
     float* stats_b = h->fuse_ln ? stats_a + h->stats_stride : nullptr;
     if ((rc = run_stack(h, h->aux, x, (int)M, ax, vp::ACT_GELU, st, stats_a, 1, stats_b, kTagAux)) != VP_OK) return rc;
   }
-  const int ph = 4 * D / c.num_heads;
+  const int ph = h->pool_ph;
   size_t need = vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph);
   size_t need_f = frame_embeddings ? vp::pool_scratch_floats(B * T, N, D, c.num_heads, ph) : 0;
   CK(h->ws_pool.ensure((need > need_f ? need : need_f) * sizeof(float)));
@@ -920,6 +950,32 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
     CK(vp::launch_pool(st, x, B * T, N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
                        h->pool_ln_g, h->pool_ln_b, normalize, static_cast<float*>(h->ws_pool.p), frame_embeddings, &h->launches));
   }
+  return VP_OK;
+}
+
+int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings, float* logits,
+                          float* global_embeddings, float* spatial_features, float* spatiotemporal_features, void* stream) {
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (h->cfg.kind != VP_KIND_CLASSIFIER) return h->fail(VP_ERR_INVALID, "handle is not a video classifier");
+  if (video == nullptr || logits == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim;
+  size_t M = 0;
+  // encoder (encoders.py:616-627); the pooler reads LN(x) in bf16 from the residual buffer
+  rc = encoder_body(h, video, VP_F32, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
+  if (rc != VP_OK) return rc;
+  const bf16* x = static_cast<const bf16*>(h->ws_x.p);
+  const int N = (int)(M / ((size_t)B * T));
+  const int ph = h->pool_ph;
+  // atten_pooler (:631-639): paddings=None, LayerNorm inside, no l2 normalisation; then projection (:643-650)
+  CK(h->ws_pool.ensure((vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph) + (size_t)B * D) * sizeof(float)));
+  float* scratch = static_cast<float*>(h->ws_pool.p);
+  float* emb = global_embeddings ? global_embeddings : scratch + vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph);
+  CK(vp::launch_pool(st, x, B, T * N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
+                     h->pool_ln_g, h->pool_ln_b, 0, scratch, emb, &h->launches));
+  CK(vp::launch_dense_f32(st, emb, h->cls_w, h->cls_b, logits, B, D, c.num_classes)); h->mark(st, "classifier_projection");
   return VP_OK;
 }
 

@@ -102,6 +102,9 @@ cudaError_t launch_row_stats(cudaStream_t s, const bf16* x, int ldx, float* stat
 cudaError_t launch_fold_ln_weight(cudaStream_t s, const float* src, const float* gamma1, const float* beta, const float* bias_in,
                                   bf16* dst, float* colsum, float* bias_out, int K, int N, int ldk, float scale);
 
+// y[rows, C] = x[rows, D] . w[D, C] + b[C], fp32 (classifier projection, encoders.py:643-650)
+cudaError_t launch_dense_f32(cudaStream_t s, const float* x, const float* w, const float* b, float* y, int rows, int D, int C);
+
 // L2 normalise rows in fp32 (encoders.py:50-67): y = x / sqrt(sum(x^2) + 1e-12)
 cudaError_t launch_l2norm(cudaStream_t s, const float* x, float* y, int rows, int D);
 

@@ -222,6 +222,26 @@ __global__ void similarity_kernel(const float* __restrict__ v, const float* __re
   if (i < Nv && j < Nt) sim[static_cast<size_t>(i) * Nt + j] = acc;
 }
 
+// y[r, c] = x[r, :] . w[:, c] + b[c]  (fp32; the classifier's `projection`, encoders.py:643-650).  w is [D, C] as Flax stores
+// Dense kernels, so threads over c read it coalesced; x[r] is staged in shared memory.  Tiny (B x D x C).
+__global__ void __launch_bounds__(256) dense_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ y, int D, int Cn) {
+  extern __shared__ float s_x[];  // [D]
+  const int r = blockIdx.y;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s_x[d] = x[static_cast<size_t>(r) * D + d];
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cn) return;
+  float a0 = 0.f, a1 = 0.f;
+  int d = 0;
+  for (; d + 1 < D; d += 2) {
+    a0 = fmaf(s_x[d], w[static_cast<size_t>(d) * Cn + c], a0);
+    a1 = fmaf(s_x[d + 1], w[static_cast<size_t>(d + 1) * Cn + c], a1);
+  }
+  if (d < D) a0 = fmaf(s_x[d], w[static_cast<size_t>(d) * Cn + c], a0);
+  y[static_cast<size_t>(r) * Cn + c] = a0 + a1 + b[c];
+}
+
 }  // namespace
 
 size_t pool_scratch_floats(int num_seq, int S, int D, int H, int dh) {
@@ -278,6 +298,12 @@ cudaError_t launch_pad_expand(cudaStream_t s, const float* frame_pad, float* pad
 cudaError_t launch_similarity(cudaStream_t s, const float* v, const float* t, float* sim, int Nv, int Nt, int D) {
   dim3 grid((Nt + 15) / 16, (Nv + 15) / 16), block(16, 16);
   similarity_kernel<<<grid, block, 0, s>>>(v, t, sim, Nv, Nt, D);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dense_f32(cudaStream_t s, const float* x, const float* w, const float* b, float* y, int rows, int D, int C) {
+  if (rows <= 0 || D <= 0 || C <= 0 || static_cast<size_t>(D) * sizeof(float) > 48 * 1024) return cudaErrorInvalidValue;
+  dense_f32_kernel<<<dim3((C + 255) / 256, rows), 256, D * sizeof(float), s>>>(x, w, b, y, D, C);
   return cudaGetLastError();
 }
 

@@ -25,7 +25,11 @@ from typing import Any, Callable, Collection, Dict, Mapping, Optional, Tuple
 import numpy as np
 
 from . import _lib
+from . import tokenizers
+from . import utils
 
+K400_NUM_CLASSES: int = 400   # models.py:51-52
+SSV2_NUM_CLASSES: int = 174
 TEXT_MAX_LEN: int = 64  # models.py:54
 TEXT_TOKENIZERS = {"c4_en": {"model_path": "gs://t5-data/vocabs/cc_en.32000/sentencepiece.model", "vocab_size": 32_000}}
 
@@ -106,7 +110,7 @@ class _Module:
             num_spatial_layers=c["num_spatial_layers"], num_temporal_layers=c["num_temporal_layers"], num_heads=c["num_heads"],
             mlp_dim=c["mlp_dim"], atten_logit_cap=float(c.get("atten_logit_cap", 0.0)),
             num_auxiliary_layers=int(c.get("num_auxiliary_layers", 0)), num_unimodal_layers=int(c.get("num_unimodal_layers", 0)),
-            vocabulary_size=int(c.get("vocabulary_size", 0)))
+            vocabulary_size=int(c.get("vocabulary_size", 0)), num_classes=int(c.get("num_classes", 0)))
 
     def _ensure_handle(self):
         if self._handle is None:
@@ -320,6 +324,54 @@ class FactorizedVideoCLIP(_Module):
         return video_emb, text_emb, outs
 
 
+class FactorizedVideoClassifier(_Module):
+    """Drop-in for encoders.FactorizedVideoClassifier (encoders.py:583-653: `encoder_params=..., num_classes=...`) and
+    encoders_mlx.FactorizedVideoClassifier (models_mlx.py:259: encoder keywords + `num_classes`).  Parameter tree:
+    `params/encoder/...`, `params/atten_pooler/...` (hidden_dim = model_dim), `params/projection/linear/{kernel,bias}`."""
+
+    _kind = _lib.VP_KIND_CLASSIFIER
+
+    def __init__(self, encoder_params: Optional[Mapping[str, Any]] = None, num_classes: int = 0, **config):
+        cfg = dict(encoder_params or {})
+        cfg.update(config)
+        if int(num_classes) <= 0:
+            raise ValueError("num_classes must be a positive integer")
+        cfg["num_classes"] = int(num_classes)
+        super().__init__(**cfg)
+        self.encoder_params = {k: v for k, v in cfg.items() if k != "num_classes"}
+        self.num_classes = int(num_classes)
+
+    def __call__(self, inputs, train: bool = False, return_intermediate: bool | Collection[str] = False, frame_paddings=None):
+        del train
+        lib = _lib.lib()
+        h = self._ensure_handle()
+        b, t, hh, ww = self._check_video(inputs)
+        p = self.config["patch_size"]
+        n, d = (hh // p) * (ww // p), self.config["model_dim"]
+        if frame_paddings is not None and tuple(frame_paddings.shape) != (b, t):
+            raise AssertionError("frame_paddings.shape == (b, t)")  # encoders.py:442
+        import torch
+        host = not _is_torch(inputs)
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)).cuda() if host else inputs
+        if not x.is_cuda:
+            raise ValueError("torch inputs must live on a CUDA device (pass numpy arrays for host buffers)")
+        x = x.to(torch.float32).contiguous()
+        names = [k for k in ("spatial_features", "spatiotemporal_features", "global_embeddings") if _contains(return_intermediate, k)]
+        shapes = {"spatial_features": (b, t * n, d), "spatiotemporal_features": (b, t * n, d), "global_embeddings": (b, d)}
+        bufs = {k: torch.empty(shapes[k], dtype=torch.float32, device=x.device) for k in names}
+        logits = torch.empty((b, self.num_classes), dtype=torch.float32, device=x.device)
+        fp = None if frame_paddings is None else torch.as_tensor(np.asarray(frame_paddings) if host else frame_paddings,
+                                                                 device=x.device).to(torch.float32).contiguous()
+        ptr = lambda k: bufs[k].data_ptr() if k in bufs else None
+        with torch.cuda.device(x.device):
+            _lib.check(lib.vp_classifier_forward(h, x.data_ptr(), b, t, hh, ww, None if fp is None else fp.data_ptr(), logits.data_ptr(),
+                                                 ptr("global_embeddings"), ptr("spatial_features"), ptr("spatiotemporal_features"),
+                                                 self._stream_ptr()), h)
+        if host:
+            return logits.cpu().numpy(), {k: a.cpu().numpy() for k, a in bufs.items()}
+        return logits, bufs
+
+
 # ------------------------------------------------------------------------------ registry (models.py:164-233)
 def videoprism_v1_base():
     return FactorizedEncoder(**CONFIGS["videoprism_v1_base"])
@@ -339,6 +391,16 @@ def videoprism_lvt_v1_large(text_tokenizer: str = "c4_en"):
     config = dict(CONFIGS["videoprism_lvt_v1_large"])
     config["vocabulary_size"] = TEXT_TOKENIZERS[text_tokenizer]["vocab_size"]
     return FactorizedVideoCLIP(**config)
+
+
+def videoprism_vc_v1_base(num_classes: int):
+    """models.py:200-205."""
+    return FactorizedVideoClassifier(encoder_params=CONFIGS["videoprism_v1_base"], num_classes=num_classes)
+
+
+def videoprism_vc_v1_large(num_classes: int):
+    """models.py:208-213."""
+    return FactorizedVideoClassifier(encoder_params=CONFIGS["videoprism_v1_large"], num_classes=num_classes)
 
 
 MODELS = {
@@ -408,6 +470,31 @@ def load_pretrained_weights(model_name: Optional[str], checkpoint_path: Optional
     return load_checkpoint(checkpoint_path)
 
 
+def load_text_tokenizer(name: str) -> tokenizers.Tokenizer:
+    """models.load_text_tokenizer (models.py:339-352)."""
+    if name not in TEXT_TOKENIZERS:
+        raise ValueError(f"Text tokenizer `{name}` not found.")
+    return tokenizers.SentencePieceTokenizer(TEXT_TOKENIZERS[name]["model_path"])
+
+
+def tokenize_texts(tokenizer: tokenizers.Tokenizer, inputs, max_length: int = TEXT_MAX_LEN, add_bos: Optional[bool] = None,
+                   canonicalize: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """models.tokenize_texts (models.py:355-407): texts -> (ids [Q, max_length] int32 zero-padded, paddings [Q, max_length]
+    float32 with 1 = padding), truncating long texts; the format `vp_clip_text_forward` takes."""
+    if canonicalize:
+        inputs = [utils.canonicalize_text(t) for t in inputs]
+    if add_bos is None:
+        add_bos = tokenizer.bos_token >= 0
+    rows = tokenizer.to_int(list(inputs), bos=add_bos, eos=False)
+    ids = np.zeros((len(rows), max_length), dtype=np.int32)
+    paddings = np.ones((len(rows), max_length), dtype=np.float32)
+    for r, toks in enumerate(rows):
+        n = min(len(toks), max_length)
+        ids[r, :n] = toks[:n]
+        paddings[r, :n] = 0.0
+    return ids, paddings
+
+
 def synthetic_state(model, seed: int = 1234) -> Dict[str, np.ndarray]:
     """Random-init fp32 parameters in the Flax key layout for a model (or model name): matrices,
     embeddings and biases N(0, 0.02), LayerNorm scale N(0, 0.1) (effective 1 + scale),
@@ -464,6 +551,51 @@ def load_model(model_name: str, weights_path: Optional[str] = None, state: Optio
             raise FileNotFoundError(f"Weights not found at {path}")
         state = load_checkpoint(path)
     model.load_state(state)
+    return model
+
+
+
+def get_model_config(model_name: str) -> dict:
+    """models_mlx.get_model_config (models_mlx.py:72-88): a copy of the named configuration."""
+    if model_name not in MODELS:
+        raise ValueError(f"Model '{model_name}' not found. Available models: {', '.join(MODELS)}")
+    return dict(get_model(model_name).config)
+
+
+def load_classifier(model_name: str, num_classes: int, weights_path: Optional[str] = None,
+                    state: Optional[Mapping[str, Any]] = None, seed: int = 0) -> FactorizedVideoClassifier:
+    """models_mlx.load_classifier (models_mlx.py:213-294): encoder backbone of `model_name` + attention pooling + a
+    `num_classes` projection.  As in the reference, a checkpoint only provides the ENCODER (`params/...` of an encoder
+    checkpoint or `params/vision_encoder/...` of a video-text one, mapped to `params/encoder/...`); pooler and head are
+    freshly initialised (Flax defaults: N(0, 0.02)-style kernels, zero biases / LayerNorm offsets) unless `state` holds them."""
+    config = get_model_config(model_name)
+    keys = ("patch_size", "pos_emb_shape", "model_dim", "num_spatial_layers", "num_temporal_layers", "num_heads", "mlp_dim",
+            "atten_logit_cap")
+    model = FactorizedVideoClassifier(encoder_params={k: config[k] for k in keys}, num_classes=num_classes)
+    flat: Dict[str, Any] = {}
+    if state is None:
+        path = weights_path or _default_weights_path(model_name)
+        if os.path.exists(path):
+            state = load_checkpoint(path)
+    if state is not None:
+        src = _flatten(state) if any(isinstance(v, Mapping) for v in state.values()) else dict(state)
+        for k, v in src.items():
+            if k.startswith("params/vision_encoder/"):
+                flat["params/encoder/" + k[len("params/vision_encoder/"):]] = v
+            elif k.startswith(("params/encoder/", "params/atten_pooler/", "params/projection/")):
+                flat[k] = v
+            elif k.startswith(("params/patch_projection", "params/spatial_", "params/temporal_")):
+                flat["params/encoder/" + k[len("params/"):]] = v
+    rng = np.random.default_rng(seed)
+    for key, shape in model.param_shapes().items():
+        if key in flat:
+            continue
+        leaf = key.rsplit("/", 1)[-1]
+        if leaf in ("bias", "b", "scale", "per_dim_scale"):
+            flat[key] = np.zeros(shape, np.float32)
+        else:
+            flat[key] = (rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02)).astype(np.float32)
+    model.load_state(flat)
     return model
 
 
