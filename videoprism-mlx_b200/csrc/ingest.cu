@@ -37,31 +37,41 @@ __device__ __forceinline__ Tap linear_tap(int d, int src, int dst, bool vertical
   return t;
 }
 
-// One block per (frame, output row): the row's vertical tap is computed once, the output row is assembled in shared
-// memory and written with coalesced 32-bit stores (byte stores and 288 redundant copies of the row tap made the first
-// version LSU-bound at 0.7 TB/s).
-__global__ void resize_frames_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int new_h,
-                                        int new_w, int y0, int x0, int target) {
-  extern __shared__ __align__(16) uint8_t row_out[];   // target * 3 bytes (padded to a multiple of 4)
-  __shared__ Tap ty_s;
-  const int y = static_cast<int>(blockIdx.x) % target;
-  const int t = static_cast<int>(blockIdx.x) / target;
+// One block per (frame, group of kRows output rows).  The horizontal taps depend only on x and the vertical ones only on
+// y, so a block computes them once into shared memory (they cost a handful of double-precision operations each; the first
+// version recomputed both for every pixel), assembles its kRows output rows there and writes them as one contiguous run of
+// 32-bit words (the rows of a group are adjacent in the output).
+constexpr int kRows = 8;
+
+__global__ void __launch_bounds__(256) resize_frames_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
+                                                               int new_h, int new_w, int y0, int x0, int target, int groups) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Tap* tx_s = reinterpret_cast<Tap*>(smem_raw);                       // [target]
+  uint8_t* rows_out = smem_raw + static_cast<size_t>(target) * sizeof(Tap);   // [kRows][target * 3]
+  __shared__ Tap ty_s[kRows];
+  const int g = static_cast<int>(blockIdx.x) % groups;
+  const int t = static_cast<int>(blockIdx.x) / groups;
+  const int ybase = g * kRows;
+  const int nrows = min(kRows, target - ybase);
   const uint8_t* frame = src + static_cast<size_t>(t) * H * W * 3;
-  const int dy = y + y0;   // coordinates in the (virtual) resized image
   const bool area2x = (W == 2 * new_w && H == 2 * new_h);
-  if (threadIdx.x == 0 && !area2x) ty_s = linear_tap(dy, H, new_h, true);
+  if (!area2x) {
+    for (int x = threadIdx.x; x < target; x += blockDim.x) tx_s[x] = linear_tap(x + x0, W, new_w, false);
+    if (threadIdx.x < nrows) ty_s[threadIdx.x] = linear_tap(ybase + threadIdx.x + y0, H, new_h, true);
+  }
   __syncthreads();
-  for (int x = threadIdx.x; x < target; x += blockDim.x) {
-    const int dx = x + x0;
-    uint8_t* o = row_out + x * 3;
+  const int row_bytes = target * 3;
+  for (int i = threadIdx.x; i < nrows * target; i += blockDim.x) {
+    const int r = i / target, x = i - r * target;
+    uint8_t* o = rows_out + r * row_bytes + x * 3;
     if (area2x) {
-      const uint8_t* p0 = frame + (static_cast<size_t>(2 * dy) * W + 2 * dx) * 3;
+      const uint8_t* p0 = frame + (static_cast<size_t>(2 * (ybase + r + y0)) * W + 2 * (x + x0)) * 3;
       const uint8_t* p1 = p0 + static_cast<size_t>(W) * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
     } else {
-      const Tap tx = linear_tap(dx, W, new_w, false);
-      const Tap ty = ty_s;
+      const Tap tx = tx_s[x];
+      const Tap ty = ty_s[r];
       const uint8_t* r0 = frame + static_cast<size_t>(ty.s0) * W * 3;
       const uint8_t* r1 = frame + static_cast<size_t>(ty.s1) * W * 3;
 #pragma unroll
@@ -73,13 +83,13 @@ __global__ void resize_frames_u8_kernel(const uint8_t* __restrict__ src, uint8_t
     }
   }
   __syncthreads();
-  const size_t row_bytes = static_cast<size_t>(target) * 3;
-  uint8_t* drow = dst + (static_cast<size_t>(t) * target + y) * row_bytes;
-  if ((reinterpret_cast<uintptr_t>(drow) & 3) == 0 && (row_bytes & 3) == 0) {
-    for (int i = threadIdx.x; i < static_cast<int>(row_bytes / 4); i += blockDim.x)
-      reinterpret_cast<uint32_t*>(drow)[i] = reinterpret_cast<const uint32_t*>(row_out)[i];
+  const int nbytes = nrows * row_bytes;
+  uint8_t* drow = dst + (static_cast<size_t>(t) * target + ybase) * row_bytes;
+  if ((reinterpret_cast<uintptr_t>(drow) & 3) == 0 && (nbytes & 3) == 0) {
+    for (int i = threadIdx.x; i < nbytes / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(drow)[i] = reinterpret_cast<const uint32_t*>(rows_out)[i];
   } else {
-    for (int i = threadIdx.x; i < static_cast<int>(row_bytes); i += blockDim.x) drow[i] = row_out[i];
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) drow[i] = rows_out[i];
   }
 }
 
@@ -95,10 +105,10 @@ cudaError_t launch_resize_frames_u8(cudaStream_t s, const uint8_t* src, int T, i
     y0 = (new_h - target) / 2;
     x0 = (new_w - target) / 2;
   }
-  const int threads = target >= 512 ? 512 : ((target + 31) / 32) * 32;
-  const size_t smem = (static_cast<size_t>(target) * 3 + 15) / 16 * 16;
-  if (smem > 48 * 1024 || static_cast<size_t>(T) * target > 0x7fffffffULL) return cudaErrorInvalidValue;
-  resize_frames_u8_kernel<<<static_cast<unsigned>(T) * target, threads, smem, s>>>(src, dst, H, W, new_h, new_w, y0, x0, target);
+  const int groups = (target + kRows - 1) / kRows;
+  const size_t smem = static_cast<size_t>(target) * sizeof(Tap) + (static_cast<size_t>(kRows) * target * 3 + 15) / 16 * 16;
+  if (smem > 48 * 1024 || static_cast<size_t>(T) * groups > 0x7fffffffULL) return cudaErrorInvalidValue;
+  resize_frames_u8_kernel<<<static_cast<unsigned>(T) * groups, 256, smem, s>>>(src, dst, H, W, new_h, new_w, y0, x0, target, groups);
   return cudaGetLastError();
 }
 
