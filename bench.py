@@ -55,7 +55,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -66,7 +66,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0=None, t1=None):
+    def stop(self, t0=None, t1=None, t_load0=None):
+        """sm_mhz / power: samples inside the timed region [t0, t1].  reasons: every throttle reason seen from the start of
+        the load (t_load0: first warm-up step, the same kernels back to back) to just after the timed region: nvidia-smi
+        refreshes its throttle flags and its (averaged) power reading more slowly than a 5-step timed region lasts."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -77,22 +80,33 @@ class ClockSampler:
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         inside = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.15)]
-        for ln in (inside or [ln for _, ln in self.lines]):
+        load = [ln for ts, ln in self.lines if t0 is None or ((t_load0 if t_load0 is not None else t0) <= ts <= t1 + 0.3)]
+        for ln in (load or [ln for _, ln in self.lines]):
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+                mx.append(float(parts[1])); power.append(float(parts[2]))
             except ValueError:
                 continue
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        power_load = power
+        power = []
+        for ln in (inside or load or [ln for _, ln in self.lines]):
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); power.append(float(parts[2]))
+            except ValueError:
+                continue
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [s for s, p in zip(sm, power) if p > 300.0] or sm
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(power)}
+                "power_w_max": max(power_load or power), "reasons_window": "first warm-up step .. end of the timed region"}
 
 
 def cpu_oracle_clips_per_s(model: str, steps: int, warmup: int, budget_s: float):
@@ -284,6 +298,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.1)   # let the first nvidia-smi sample land before the load starts
+    t_load0 = time.time()
     for i in range(warmup):
         step(i)
     barrier()
@@ -296,7 +312,7 @@ def main():
     end.record()
     barrier()
     ms = start.elapsed_time(end)
-    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
+    clocks = sampler.stop(t_wall0, time.time(), t_load0) if rank == 0 else None
     launches = model.kernel_launches - launches0
     t = torch.tensor([ms], device="cuda")
     if world > 1:

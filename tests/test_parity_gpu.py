@@ -278,3 +278,24 @@ def test_load_classifier_takes_the_encoder_of_a_video_text_checkpoint(tmp_path):
     logits, outs = m(v, return_intermediate=True)
     assert logits.shape == (2, 5) and np.isfinite(logits).all()
     assert np.array_equal(outs["spatiotemporal_features"], couts["spatiotemporal_features"])
+
+
+def test_batches_larger_than_one_pass_are_split_on_the_device_path():
+    """The device entry point runs at most 2^18 tokens per pass (32-bit indices, bounded workspace) and loops over the
+    rest: a 4100-clip tiny batch (4096 + 4) equals the two halves run separately, bit for bit, including
+    spatial_features and frame_paddings."""
+    cfg = O.tiny_config("encoder")
+    W = O.make_synthetic_weights(cfg)
+    m = make_model(cfg)
+    B = 4100
+    v = torch.from_numpy(O.make_video(B, 4, 16, seed=9, kind="normal")).cuda()
+    fp = torch.zeros((B, 4), device="cuda")
+    fp[4097, 2:] = 1
+    fp[5, 1:] = 1
+    out, outs = m.apply(W, v, train=False, return_intermediate=True, frame_paddings=fp)
+    assert out.shape == (B, 4 * 16, cfg["model_dim"])
+    a, ao = m(v[:4096], return_intermediate=True, frame_paddings=fp[:4096])
+    b, bo = m(v[4096:], return_intermediate=True, frame_paddings=fp[4096:])
+    assert torch.equal(out[:4096], a) and torch.equal(out[4096:], b)
+    assert torch.equal(outs["spatial_features"][4096:], bo["spatial_features"])
+    assert torch.isfinite(out).all()

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <string>
@@ -800,8 +801,27 @@ static int encoder_forward_dev(vp_handle* h, const void* video, int in_dtype, in
   if (out_dtype != VP_F32 && out_dtype != VP_BF16) return h->fail(VP_ERR_INVALID, "out_dtype must be VP_F32 or VP_BF16");
   if (spatial_features != nullptr && out_dtype != VP_F32) return h->fail(VP_ERR_UNSUPPORTED, "spatial_features requires VP_F32 outputs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return encoder_body(h, video, in_dtype, B, T, H, W, frame_paddings, out_dtype == VP_F32 ? static_cast<float*>(out_features) : nullptr,
-                      out_dtype == VP_BF16 ? static_cast<bf16*>(out_features) : nullptr, false, static_cast<float*>(spatial_features), st, nullptr);
+  // Clips are independent (encoders.py:434-436 only folds B into the leading axis), so a batch larger than one pass can
+  // hold (32-bit element indices, bounded workspace: at most 2^18 tokens = 64 clips of 16 x 256) runs as consecutive
+  // passes on the same stream; the results are bitwise those of a single pass.
+  const int P = h->cfg.patch_size;
+  if (B <= 0 || T <= 0 || P <= 0 || H % P || W % P || H != W)   // encoder_body reports the precise reason
+    return encoder_body(h, video, in_dtype, B, T, H, W, frame_paddings, nullptr, nullptr, false, nullptr, st, nullptr);
+  const size_t tokens_per_clip = (size_t)T * (H / P) * (W / P);
+  const size_t D = h->cfg.model_dim;
+  const int max_clips = (int)std::max<size_t>(1, ((size_t)1 << 18) / tokens_per_clip);
+  const size_t in_elem = in_dtype == VP_U8 ? 1 : sizeof(float), out_elem = out_dtype == VP_F32 ? sizeof(float) : sizeof(bf16);
+  for (int b0 = 0; b0 < B; b0 += max_clips) {
+    const int bc = std::min(max_clips, B - b0);
+    const char* vin = static_cast<const char*>(video) + (size_t)b0 * T * H * W * 3 * in_elem;
+    char* o = static_cast<char*>(out_features) + (size_t)b0 * tokens_per_clip * D * out_elem;
+    float* sp = spatial_features ? static_cast<float*>(spatial_features) + (size_t)b0 * tokens_per_clip * D : nullptr;
+    rc = encoder_body(h, vin, in_dtype, bc, T, H, W, frame_paddings ? frame_paddings + (size_t)b0 * T : nullptr,
+                      out_dtype == VP_F32 ? reinterpret_cast<float*>(o) : nullptr, out_dtype == VP_BF16 ? reinterpret_cast<bf16*>(o) : nullptr,
+                      false, sp, st, nullptr);
+    if (rc != VP_OK) return rc;
+  }
+  return VP_OK;
 }
 
 int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
