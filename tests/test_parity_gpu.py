@@ -299,3 +299,62 @@ def test_batches_larger_than_one_pass_are_split_on_the_device_path():
     assert torch.equal(out[:4096], a) and torch.equal(out[4096:], b)
     assert torch.equal(outs["spatial_features"][4096:], bo["spatial_features"])
     assert torch.isfinite(out).all()
+
+
+def test_config2_full_batch_properties():
+    """BASELINE.json configs[1] at its full size (base encoder, 32 clips of 16x288x288x3), through properties that do not
+    need a 32-clip CPU oracle run: (i) clip 0 of the batch equals the reference-generated golden of configs[0] (same clip,
+    same weights) to the token bar; (ii) permuting the clips permutes the outputs bit for bit (clips are independent,
+    encoders.py:434-436); (iii) the host (numpy, chunk-pipelined) and device entry points agree bit for bit;
+    (iv) every output is finite and LayerNorm-scaled (temporal_ln: per-token variance of O(1))."""
+    import os
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    m = vp.get_model("videoprism_public_v1_base")
+    m.load_state(O.make_synthetic_weights(cfg))
+    B = 32
+    v = np.concatenate([O.make_video(1, 16, 288, seed=0), O.make_video(B - 1, 16, 288, seed=21)], axis=0)
+    vd = torch.from_numpy(v).cuda()
+    out, _ = m(vd)
+    assert out.shape == (B, 4096, 768) and torch.isfinite(out).all()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "base_config1.npz"))
+    stride = int(g["token_stride"])
+    c, _ = report("config-2 batch, clip 0 vs reference golden", out[0:1, ::stride].cpu().numpy(), g["features_sample"])
+    assert c >= COS_MIN
+    perm = torch.from_numpy(np.random.default_rng(3).permutation(B)).cuda()
+    out_p, _ = m(vd[perm].contiguous())
+    assert torch.equal(out_p, out[perm])
+    host, _ = m(v)
+    assert np.array_equal(host, out.cpu().numpy())
+    var = out.float().var(dim=-1)
+    assert 0.2 < float(var.min()) and float(var.max()) < 5.0
+
+
+def test_text_tower_edge_cases():
+    """Ragged text batches (the reference pads to 64 and marks paddings, models.py:385-407): a query with a single real
+    token, a full-length query without padding, one query alone (Q = 1) and a batch whose rows are processed identically
+    whatever their neighbours are (row independence, bit for bit)."""
+    cfg = O.tiny_config("clip")
+    W = O.make_synthetic_weights(cfg)
+    m = make_model(cfg)
+    L = 8
+    rng = np.random.default_rng(4)
+    ids = rng.integers(1, cfg["vocabulary_size"], (5, L)).astype(np.int32)
+    lens = np.array([1, L, 3, L - 1, 2])
+    pad = (np.arange(L)[None, :] >= lens[:, None]).astype(np.float32)
+    ids = np.where(pad > 0, 0, ids).astype(np.int32)
+    _, want, _ = O.run_clip(cfg, W, None, ids, pad)
+    _, got, _ = m.apply(W, None, ids, pad, train=False)
+    assert got.shape == (5, cfg["model_dim"])
+    assert report("text tower, ragged lengths 1..L", got, want)[0] >= COS_MIN
+    np.testing.assert_allclose(np.linalg.norm(got, axis=-1), 1.0, atol=1e-5)
+    for q in (0, 1, 4):
+        _, one, _ = m(None, ids[q:q + 1], pad[q:q + 1])
+        assert np.array_equal(one[0], got[q])
+    _, raw, _ = m(None, ids, pad, normalize=False)
+    _, wraw, _ = O.run_clip(cfg, W, None, ids, pad, normalize=False)
+    assert report("text tower, unnormalised", raw, wraw)[0] >= COS_MIN
+    v_none, t_none, outs = m(None, None, None)
+    assert v_none is None and t_none is None and outs == {}
+    with pytest.raises(AssertionError):
+        m(None, ids, None)            # encoders.py:888
