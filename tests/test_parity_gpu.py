@@ -358,3 +358,20 @@ def test_text_tower_edge_cases():
     assert v_none is None and t_none is None and outs == {}
     with pytest.raises(AssertionError):
         m(None, ids, None)            # encoders.py:888
+
+
+def test_fprop_dtype_bfloat16_returns_bf16_features():
+    """models.get_model(name, fprop_dtype=jnp.bfloat16) (models.py:283-301): bfloat16 features on the device path, equal
+    to the float32 features rounded once (the same LayerNorm result, stored narrower)."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    W = O.make_synthetic_weights(cfg)
+    v = torch.from_numpy(O.make_video(2, 16, 288, seed=12)).cuda()
+    m32 = vp.get_model("videoprism_public_v1_base")
+    m16 = vp.get_model("videoprism_public_v1_base", fprop_dtype=torch.bfloat16)
+    f32, _ = m32.apply(W, v, train=False)
+    b16, _ = m16.apply(W, v, train=False)
+    assert f32.dtype == torch.float32 and b16.dtype == torch.bfloat16 and b16.shape == f32.shape
+    assert torch.equal(b16, f32.to(torch.bfloat16))
+    host, _ = m16.apply(W, v.cpu().numpy(), train=False)      # numpy callers keep float32
+    assert host.dtype == np.float32 and np.array_equal(host, f32.cpu().numpy())

@@ -306,6 +306,27 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const AttnArgs a, int t
   warp_store_out<DH>(st, sQ[warp], sQa, 0, lane, a.out, a.ldo, row_first, rstride, a.S, col0);
 }
 
+// Sequences whose keys are ALL padded (a padded frame in the spatial stack): every logit becomes min_value
+// (layers.py:155-179), the softmax is uniform, and each query row receives the mean of V.  Lets frame-padded batches keep
+// the tcgen05 kernel: it runs unmasked on every frame and this kernel overwrites the (rare) padded ones.
+// grid (num_seq, heads), block 256 = 4 row groups x 64 lanes (2 bf16 each for dh = 64... one per lane pair for dh = 32).
+__global__ void __launch_bounds__(256) attn_uniform_rows_kernel(const AttnArgs a) {
+  const int seq = blockIdx.x, h = blockIdx.y;
+  if (a.key_pad[static_cast<size_t>(seq) * a.S] < 0.5f) return;
+  __shared__ float part[4][64];
+  const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const size_t row0 = static_cast<size_t>(seq / a.group) * a.S * a.group + (seq % a.group);
+  float acc = 0.f;
+  if (j < a.dh)
+    for (int s = g; s < a.S; s += 4) acc += __bfloat162float(a.v[(row0 + static_cast<size_t>(s) * a.group) * a.ld + h * a.dh + j]);
+  part[g][j] = acc;
+  __syncthreads();
+  if (j < a.dh) {
+    const bf16 m = __float2bfloat16((part[0][j] + part[1][j] + part[2][j] + part[3][j]) / static_cast<float>(a.S));
+    for (int s = g; s < a.S; s += 4) a.out[(row0 + static_cast<size_t>(s) * a.group) * a.ldo + h * a.dh + j] = m;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_attention_tcgen05(cudaStream_t s, const AttnArgs& a);
@@ -314,6 +335,19 @@ cudaError_t launch_attention_long_tcgen05(cudaStream_t s, const AttnArgs& a);
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (a.num_seq <= 0 || a.S <= 0) return cudaSuccess;
   if ((a.ld % 8) || (a.ldo % 8) || (a.dh != 64 && a.dh != 32) || a.group < 1) return cudaErrorInvalidValue;
+  if (a.launched) *a.launched = 1;
+  if (!a.force_mma_sync && a.key_pad != nullptr && a.pad_whole_seq && !a.causal) {
+    AttnArgs b = a;
+    b.key_pad = nullptr;
+    cudaError_t e = launch_attention_tcgen05(s, b);   // unmasked fast path on every sequence ...
+    if (e == cudaErrorNotSupported) e = launch_attention_long_tcgen05(s, b);
+    if (e == cudaSuccess) {                           // ... then the fully padded sequences get the uniform-softmax result
+      attn_uniform_rows_kernel<<<dim3(a.num_seq, a.heads), 256, 0, s>>>(a);
+      if (a.launched) *a.launched = 2;
+      return cudaGetLastError();
+    }
+    if (e != cudaErrorNotSupported) return e;
+  }
   if (!a.force_mma_sync) {
     const cudaError_t e = launch_attention_tcgen05(s, a);   // S = 256, dh = 64, unmasked: the spatial stack
     if (e != cudaErrorNotSupported) return e;

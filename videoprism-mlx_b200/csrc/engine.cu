@@ -513,6 +513,7 @@ struct SeqLayout {
   int num_seq, S, group, causal;
   const float* key_pad;    // [num_seq, S] or null
   const float* row_scale;  // [M] or null
+  int pad_whole_seq = 0;   // key_pad is constant within a sequence (frame paddings seen by the spatial stack)
 };
 
 // One Transformer stack (layers.py:989-1041) over the bf16 residual stream x [M, D] (in place).
@@ -545,8 +546,11 @@ int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayo
     vp::AttnArgs at;
     at.q = qkv; at.k = qkv + D; at.v = qkv + 2 * D; at.ld = 3 * D; at.out = n; at.ldo = D;
     at.num_seq = sl.num_seq; at.S = sl.S; at.group = sl.group; at.heads = H; at.dh = D / H;
-    at.cap = h->cfg.atten_logit_cap; at.key_pad = sl.key_pad; at.causal = sl.causal;
+    at.cap = h->cfg.atten_logit_cap; at.key_pad = sl.key_pad; at.causal = sl.causal; at.pad_whole_seq = sl.pad_whole_seq;
+    int n_attn = 1;
+    at.launched = &n_attn;
     CK(vp::launch_attention(st, at)); h->mark(st, tag[2]);
+    h->launches += n_attn - 1;
     vp::GemmEpilogue e2;
     e2.bias = w.bo + (size_t)l * D; e2.resid = x; e2.ldr = D;
     if (fuse) e2.stats_out = stats_b;
@@ -637,7 +641,7 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
   CK(vp::launch_gemm(st, patches, h->k_patch_pad, h->w_patch, h->k_patch_pad, x, D, (int)M, D, h->k_patch_pad, ep)); h->mark(st, "patch_proj");
 
   // spatial stack: sequences = frames (N contiguous tokens)
-  SeqLayout sp{B * T, N, 1, 0, pad_tok, keep_tok};
+  SeqLayout sp{B * T, N, 1, 0, pad_tok, keep_tok, /*pad_whole_seq=*/1};   // a frame is padded as a whole (encoders.py:440-447)
   if ((rc = run_stack(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st, stats_a, vp::gemm_stats_slots(D), stats_b, kTagSpatial)) != VP_OK) return rc;
 
   // spatial_ln (+ temporal pos-emb add, encoders.py:528-553); in place on the residual stream

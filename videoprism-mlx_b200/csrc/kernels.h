@@ -83,6 +83,8 @@ struct AttnArgs {
   const float* key_pad = nullptr;
   int causal = 0;
   int force_mma_sync = 0;   // tests: bypass the tcgen05 kernel
+  int pad_whole_seq = 0;    // key_pad is constant within every sequence (frame paddings in the spatial stack)
+  int* launched = nullptr;  // optional: number of kernels launch_attention enqueued
 };
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a);
 

@@ -195,6 +195,13 @@ class _Module:
         import torch
         return int(torch.cuda.current_stream().cuda_stream)
 
+    def _wants_bf16(self) -> bool:
+        """`get_model(name, fprop_dtype=jnp.bfloat16)` (models.py:283-301) makes the reference emit bfloat16 features; the
+        device-buffer path honours that (the features leave the last LayerNorm in bf16, half the write traffic).  Host
+        (numpy) results stay float32: numpy has no bfloat16."""
+        d = self.fprop_dtype
+        return d is not None and "bfloat16" in (getattr(d, "__name__", None) or str(d))
+
     def _check_video(self, inputs) -> Tuple[int, int, int, int]:
         if inputs.ndim != 5 or inputs.shape[-1] != 3:
             raise ValueError(f"inputs must be [B, T, H, W, 3], got {tuple(inputs.shape)}")
@@ -232,13 +239,14 @@ class FactorizedEncoder(_Module):
             is_u8 = inputs.dtype == torch.uint8     # raw decoded frames: / 255 happens on the device (video_utils.py:88-93)
             x = inputs.contiguous() if is_u8 else inputs.to(torch.float32).contiguous()
             fwd = lib.vp_encoder_forward_u8 if is_u8 else lib.vp_encoder_forward
-            out = torch.empty((b, t * n, d), dtype=torch.float32, device=x.device)
+            bf16_out = self._wants_bf16() and not want_spatial
+            out = torch.empty((b, t * n, d), dtype=torch.bfloat16 if bf16_out else torch.float32, device=x.device)
             sp = torch.empty_like(out) if want_spatial else None
             fp = None if frame_paddings is None else torch.as_tensor(frame_paddings, device=x.device).to(torch.float32).contiguous()
             with torch.cuda.device(x.device):
                 _lib.check(fwd(h, x.data_ptr(), b, t, hh, ww, None if fp is None else fp.data_ptr(),
-                                                  out.data_ptr(), None if sp is None else sp.data_ptr(), _lib.VP_F32,
-                                                  self._stream_ptr()), h)
+                                                  out.data_ptr(), None if sp is None else sp.data_ptr(),
+                                                  _lib.VP_BF16 if bf16_out else _lib.VP_F32, self._stream_ptr()), h)
             outs = {"spatial_features": sp} if want_spatial else {}
             return out, outs
         is_u8 = np.asarray(inputs).dtype == np.uint8
