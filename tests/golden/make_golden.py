@@ -87,6 +87,21 @@ def tiny_cases():
                 arrays[k] = np.asarray(a)
     save("clip_tiny", **arrays)
     classifier_case()
+    giant_head_case()
+
+
+def giant_head_case():
+    # the giant configurations (models.py:105-115) have dim_per_head = 1408 / 16 = 88: tiny encoder with the same head
+    # width (model_dim 176, 2 heads), 16 tokens per frame, 5 frames, a padded frame
+    cfg = O.tiny_config("encoder", model_dim=176, num_heads=2, mlp_dim=352)
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 5, 16, seed=15, kind="normal")
+    fp = np.zeros((2, 5), np.float32); fp[1, 3:] = 1
+    m = encoders.FactorizedEncoder(scan=True, **{k: x for k, x in cfg.items() if k != "kind"})
+    out, outs = m.apply(tree_of(W), jnp.asarray(v), train=False, return_intermediate=True)
+    outp, _ = m.apply(tree_of(W), jnp.asarray(v), train=False, frame_paddings=jnp.asarray(fp))
+    save("enc_tiny_dh88", features=np.asarray(out), spatial_features=np.asarray(outs["spatial_features"]),
+         features_frame_paddings=np.asarray(outp), frame_paddings=fp)
 
 
 def classifier_case():
@@ -135,6 +150,9 @@ def full_size_cases():
 if __name__ == "__main__":
     if "--classifier-only" in sys.argv:
         classifier_case()
+        sys.exit(0)
+    if "--dh88-only" in sys.argv:
+        giant_head_case()
         sys.exit(0)
     tiny_cases()
     if "--tiny-only" not in sys.argv:

@@ -53,6 +53,19 @@ def test_tiny_clip():
     assert np.abs(ve - g["video_emb_raw"]).max() <= FEAT_TOL and np.abs(te - g["text_emb_raw"]).max() <= FEAT_TOL
 
 
+def test_tiny_encoder_giant_head_width():
+    """dim_per_head = 88 as in the giant configurations (models.py:105-115), 5 frames (temporal table 4 -> 5), paddings."""
+    g = load("enc_tiny_dh88")
+    cfg = O.tiny_config("encoder", model_dim=176, num_heads=2, mlp_dim=352)
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 5, 16, seed=15, kind="normal")
+    out, outs = O.run_encoder(cfg, W, v, return_intermediate=True)
+    assert np.abs(out - g["features"]).max() <= FEAT_TOL
+    assert np.abs(outs["spatial_features"] - g["spatial_features"]).max() <= FEAT_TOL
+    outp, _ = O.run_encoder(cfg, W, v, frame_paddings=torch.from_numpy(g["frame_paddings"]))
+    assert np.abs(outp - g["features_frame_paddings"]).max() <= FEAT_TOL
+
+
 def test_tiny_classifier():
     """encoders_test.py:183-231 shapes: FactorizedVideoClassifier through the reference's own code."""
     g = load("classifier_tiny")

@@ -114,3 +114,18 @@ def test_tiny_classifier_case():
     import torch
     lt, _ = m(torch.from_numpy(v).cuda())
     assert np.array_equal(lt.cpu().numpy(), logits)
+
+
+def test_tiny_encoder_giant_head_width():
+    """dim_per_head = 88 (the giant configurations, models.py:105-115): generic attention kernels with zero-padded head
+    tiles, GEMMs with K = 176 (not a multiple of the 64-wide K block) and N = 176 (partial 128-column tiles)."""
+    g = np.load(os.path.join(G, "enc_tiny_dh88.npz"))
+    cfg = O.tiny_config("encoder", model_dim=176, num_heads=2, mlp_dim=352)
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 5, 16, seed=15, kind="normal")
+    m = model_for(cfg)
+    out, outs = m.apply(W, v, train=False, return_intermediate=True)
+    check("tiny encoder dh=88", out, g["features"])
+    check("  spatial_features", outs["spatial_features"], g["spatial_features"])
+    outp, _ = m.apply(W, v, train=False, frame_paddings=g["frame_paddings"])
+    check("  with frame_paddings", outp, g["features_frame_paddings"])

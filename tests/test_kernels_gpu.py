@@ -256,6 +256,12 @@ def ref_attention(qkv, num_seq, S, group, heads, dh, cap, key_pad, causal):
     (2, 1024, 1, 4, 64, 2, False),      # the same long sequence on the mma.sync flash kernel
     (3, 16, 1, 2, 32, 0, True),
     (5, 100, 1, 2, 32, 1, True),
+    (6, 256, 1, 16, 88, 0, False),      # giant configuration's head width (models.py:105-115): dim_per_head = 88, zero-padded tiles
+    (3, 256, 1, 4, 88, 0, True),        # ... with key paddings (one fully padded sequence)
+    (2 * 64, 16, 64, 4, 88, 0, True),   # ... temporal tubes, strided, padded frames
+    (4, 65, 1, 2, 88, 1, True),         # ... causal + paddings, ragged S
+    (3, 130, 1, 2, 104, 0, False),      # another non-power-of-two head width (13 chunks), ragged S
+    (2, 70, 1, 2, 128, 0, False),       # full-width tiles
 ])
 def test_attention(L, num_seq, S, group, heads, dh, causal, pad):
     g = torch.Generator(device="cuda").manual_seed(S + heads)

@@ -84,6 +84,10 @@ def test_classifier_registry_and_config_surface():
     assert models.videoprism_vc_v1_large(num_classes=7).config["num_spatial_layers"] == 24
     with pytest.raises(ValueError):
         vp.FactorizedVideoClassifier(encoder_params=models.CONFIGS["videoprism_v1_base"], num_classes=0)
+    giant = models.videoprism_v1_giant()
+    assert giant.config["model_dim"] == 1408 and giant.config["model_dim"] // giant.config["num_heads"] == 88
+    assert models.videoprism_vc_v1_giant(num_classes=3).config["num_spatial_layers"] == 40
+    assert models.videoprism_lvt_v1_giant().config["norm_policy"] == "primer_hybrid"
     cfg = models.get_model_config("videoprism_lvt_public_v1_base")
     assert cfg["num_auxiliary_layers"] == 2 and cfg["vocabulary_size"] == 32000
     with pytest.raises(ValueError):

@@ -25,6 +25,7 @@ constexpr float kMasked = -1.0e30f;  // finite: a fully masked row becomes unifo
 template <int DH>
 __device__ __forceinline__ uint32_t swz(int r, int c) {
   // byte offset of 16-byte chunk c of row r in a [rows][DH] bf16 tile (conflict-free for ldmatrix)
+  if (DH == 128) return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4));
   if (DH == 64) return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
   return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
@@ -153,7 +154,8 @@ __device__ __forceinline__ void warp_load_q_frags(uint32_t (&qf)[DH / 16][4], ui
 // normalise, stage through smem (rows row_base..+15 of sO, this warp only), 16-byte stores
 template <int DH>
 __device__ __forceinline__ void warp_store_out(WarpState<DH>& st, uint8_t* sO_gen, uint32_t sO, int row_base, int lane,
-                                               bf16* out, int ldo, size_t row_first, int row_stride, int valid_rows, int col0) {
+                                               bf16* out, int ldo, size_t row_first, int row_stride, int valid_rows, int col0,
+                                               int real_chunks) {
   float l0 = st.l[0], l1 = st.l[1];
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -170,7 +172,7 @@ __device__ __forceinline__ void warp_store_out(WarpState<DH>& st, uint8_t* sO_ge
   constexpr int CPR = DH / 8;  // 16-byte chunks per row
   for (int idx = lane; idx < 16 * CPR; idx += 32) {
     const int r = idx / CPR, ch = idx % CPR;
-    if (r < valid_rows) {
+    if (r < valid_rows && ch < real_chunks) {
       const uint4 v = *reinterpret_cast<const uint4*>(sO_gen + swz<DH>(row_base + r, ch));
       *reinterpret_cast<uint4*>(out + (row_first + static_cast<size_t>(r) * row_stride) * ldo + col0 + ch * 8) = v;
     }
@@ -181,11 +183,15 @@ __device__ __forceinline__ void warp_store_out(WarpState<DH>& st, uint8_t* sO_ge
 // ---------------------------------------------------------------- flash kernel
 template <int DH>
 __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a) {
+  // DH is the padded head dimension of the smem tiles; a.dh (<= DH, a multiple of 8) the real one: 16-byte chunks past
+  // it are zero-filled on load (they add nothing to q.k and give zero context columns) and never stored.
   constexpr int BQ = 64, BKV = 64, CPR = DH / 8;
-  __shared__ __align__(128) uint8_t sQ[BQ * DH * 2];
-  __shared__ __align__(128) uint8_t sK[2][BKV * DH * 2];
-  __shared__ __align__(128) uint8_t sV[2][BKV * DH * 2];
-  __shared__ float sFlag[2][BKV];
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  uint8_t* sQ = attn_smem;
+  uint8_t(*sK)[BKV * DH * 2] = reinterpret_cast<uint8_t(*)[BKV * DH * 2]>(attn_smem + BQ * DH * 2);
+  uint8_t(*sV)[BKV * DH * 2] = reinterpret_cast<uint8_t(*)[BKV * DH * 2]>(attn_smem + BQ * DH * 2 + 2 * BKV * DH * 2);
+  float(*sFlag)[BKV] = reinterpret_cast<float(*)[BKV]>(attn_smem + BQ * DH * 2 + 4 * BKV * DH * 2);
+  const int real_chunks = a.dh / 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nqb = (a.S + BQ - 1) / BQ;
@@ -194,15 +200,15 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a) {
   const int sid = blockIdx.x / nqb;
   const size_t row_first = static_cast<size_t>(sid / a.group) * a.group * a.S + (sid % a.group);
   const int rstride = a.group;
-  const int col0 = h * DH;
+  const int col0 = h * a.dh;
   const uint32_t sQa = smem_u32(sQ);
 
   // Q tile
   for (int idx = tid; idx < BQ * CPR; idx += 128) {
     const int r = idx / CPR, ch = idx % CPR;
     const int qi = q0 + r;
-    const bool ok = qi < a.S;
-    const bf16* src = a.q + (row_first + static_cast<size_t>(ok ? qi : 0) * rstride) * a.ld + col0 + ch * 8;
+    const bool ok = qi < a.S && ch < real_chunks;
+    const bf16* src = a.q + (row_first + static_cast<size_t>(ok ? qi : 0) * rstride) * a.ld + col0 + (ok ? ch : 0) * 8;
     cp_async16(sQa + swz<DH>(r, ch), src, ok);
   }
   auto load_kv = [&](int tile, int buf) {
@@ -211,10 +217,10 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a) {
     for (int idx = tid; idx < BKV * CPR; idx += 128) {
       const int r = idx / CPR, ch = idx % CPR;
       const int kj = k0 + r;
-      const bool ok = kj < a.S;
+      const bool ok = kj < a.S && ch < real_chunks;
       const size_t row = row_first + static_cast<size_t>(ok ? kj : 0) * rstride;
-      cp_async16(sKa + swz<DH>(r, ch), a.k + row * a.ld + col0 + ch * 8, ok);
-      cp_async16(sVa + swz<DH>(r, ch), a.v + row * a.ld + col0 + ch * 8, ok);
+      cp_async16(sKa + swz<DH>(r, ch), a.k + row * a.ld + col0 + (ok ? ch : 0) * 8, ok);
+      cp_async16(sVa + swz<DH>(r, ch), a.v + row * a.ld + col0 + (ok ? ch : 0) * 8, ok);
     }
     if (a.key_pad != nullptr && tid < BKV) {
       const int kj = k0 + tid;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a) {
   const int valid = min(16, a.S - (q0 + warp * 16));
   if (valid > 0) {
     warp_store_out<DH>(st, sQ, sQa, warp * 16, lane, a.out, a.ldo, row_first + static_cast<size_t>(q0 + warp * 16) * rstride,
-                       rstride, valid, col0);
+                       rstride, valid, col0, real_chunks);
   }
 }
 
@@ -264,22 +270,24 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a) {
 template <int DH>
 __global__ void __launch_bounds__(128) attn_small_kernel(const AttnArgs a, int total_problems) {
   constexpr int CPR = DH / 8;
-  __shared__ __align__(128) uint8_t sQ[4][16 * DH * 2];
-  __shared__ __align__(128) uint8_t sK[4][16 * DH * 2];
-  __shared__ __align__(128) uint8_t sV[4][16 * DH * 2];
-  __shared__ float sFlag[4][16];
+  constexpr int WPB = DH > 64 ? 2 : 4;   // warps (problems) per block: 3 tiles of 16 x DH bf16 each, within 48 KB of static smem
+  __shared__ __align__(128) uint8_t sQ[WPB][16 * DH * 2];
+  __shared__ __align__(128) uint8_t sK[WPB][16 * DH * 2];
+  __shared__ __align__(128) uint8_t sV[WPB][16 * DH * 2];
+  __shared__ float sFlag[WPB][16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int prob = blockIdx.x * 4 + warp;  // = sid * heads + h
+  const int real_chunks = a.dh / 8;
+  const int prob = blockIdx.x * WPB + warp;  // = sid * heads + h
   if (prob >= total_problems) return;
   const int sid = prob / a.heads, h = prob % a.heads;
   const size_t row_first = static_cast<size_t>(sid / a.group) * a.group * a.S + (sid % a.group);
   const int rstride = a.group;
-  const int col0 = h * DH;
+  const int col0 = h * a.dh;
   const uint32_t sQa = smem_u32(sQ[warp]), sKa = smem_u32(sK[warp]), sVa = smem_u32(sV[warp]);
   for (int idx = lane; idx < 16 * CPR; idx += 32) {
     const int r = idx / CPR, ch = idx % CPR;
-    const bool ok = r < a.S;
-    const size_t off = (row_first + static_cast<size_t>(ok ? r : 0) * rstride) * a.ld + col0 + ch * 8;
+    const bool ok = r < a.S && ch < real_chunks;
+    const size_t off = (row_first + static_cast<size_t>(ok ? r : 0) * rstride) * a.ld + col0 + (ok ? ch : 0) * 8;
     cp_async16(sQa + swz<DH>(r, ch), a.q + off, ok);
     cp_async16(sKa + swz<DH>(r, ch), a.k + off, ok);
     cp_async16(sVa + swz<DH>(r, ch), a.v + off, ok);
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const AttnArgs a, int t
   warp_load_q_frags<DH>(qf, sQa, 0, lane);
   warp_attend_tile<DH, 2>(st, qf, sKa, sVa, 0, a.S, a.cap, a.key_pad != nullptr ? sFlag[warp] : nullptr, a.causal != 0, qi0, qi1,
                           qpad0, qpad1, lane);
-  warp_store_out<DH>(st, sQ[warp], sQa, 0, lane, a.out, a.ldo, row_first, rstride, a.S, col0);
+  warp_store_out<DH>(st, sQ[warp], sQa, 0, lane, a.out, a.ldo, row_first, rstride, a.S, col0, real_chunks);
 }
 
 // Sequences whose keys are ALL padded (a padded frame in the spatial stack): every logit becomes min_value
@@ -314,16 +322,20 @@ __global__ void __launch_bounds__(256) attn_uniform_rows_kernel(const AttnArgs a
   const int seq = blockIdx.x, h = blockIdx.y;
   if (a.key_pad[static_cast<size_t>(seq) * a.S] < 0.5f) return;
   __shared__ float part[4][64];
-  const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int g = threadIdx.x >> 6;
   const size_t row0 = static_cast<size_t>(seq / a.group) * a.S * a.group + (seq % a.group);
-  float acc = 0.f;
-  if (j < a.dh)
-    for (int s = g; s < a.S; s += 4) acc += __bfloat162float(a.v[(row0 + static_cast<size_t>(s) * a.group) * a.ld + h * a.dh + j]);
-  part[g][j] = acc;
-  __syncthreads();
-  if (j < a.dh) {
-    const bf16 m = __float2bfloat16((part[0][j] + part[1][j] + part[2][j] + part[3][j]) / static_cast<float>(a.S));
-    for (int s = g; s < a.S; s += 4) a.out[(row0 + static_cast<size_t>(s) * a.group) * a.ldo + h * a.dh + j] = m;
+  for (int j0 = 0; j0 < a.dh; j0 += 64) {
+    const int j = j0 + (threadIdx.x & 63);
+    float acc = 0.f;
+    if (j < a.dh)
+      for (int s = g; s < a.S; s += 4) acc += __bfloat162float(a.v[(row0 + static_cast<size_t>(s) * a.group) * a.ld + h * a.dh + j]);
+    part[g][j - j0] = acc;
+    __syncthreads();
+    if (j < a.dh) {
+      const bf16 m = __float2bfloat16((part[0][j - j0] + part[1][j - j0] + part[2][j - j0] + part[3][j - j0]) / static_cast<float>(a.S));
+      for (int s = g; s < a.S; s += 4) a.out[(row0 + static_cast<size_t>(s) * a.group) * a.ldo + h * a.dh + j] = m;
+    }
+    __syncthreads();
   }
 }
 
@@ -334,7 +346,9 @@ cudaError_t launch_attention_long_tcgen05(cudaStream_t s, const AttnArgs& a);
 
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (a.num_seq <= 0 || a.S <= 0) return cudaSuccess;
-  if ((a.ld % 8) || (a.ldo % 8) || (a.dh != 64 && a.dh != 32) || a.group < 1) return cudaErrorInvalidValue;
+  if ((a.ld % 8) || (a.ldo % 8) || a.dh <= 0 || (a.dh % 8) || a.dh > 128 || a.group < 1) return cudaErrorInvalidValue;
+  // smem tile width: 32 / 64 exactly, anything else (e.g. the giant configuration's dim_per_head = 88) zero-padded to 128
+  const int DHT = a.dh == 32 ? 32 : a.dh == 64 ? 64 : 128;
   if (a.launched) *a.launched = 1;
   if (!a.force_mma_sync && a.key_pad != nullptr && a.pad_whole_seq && !a.causal) {
     AttnArgs b = a;
@@ -356,13 +370,23 @@ cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   }
   if (a.S <= 16) {
     const int total = a.num_seq * a.heads;
-    const int grid = (total + 3) / 4;
-    if (a.dh == 64) attn_small_kernel<64><<<grid, 128, 0, s>>>(a, total);
-    else attn_small_kernel<32><<<grid, 128, 0, s>>>(a, total);
+    if (DHT == 64) attn_small_kernel<64><<<(total + 3) / 4, 128, 0, s>>>(a, total);
+    else if (DHT == 32) attn_small_kernel<32><<<(total + 3) / 4, 128, 0, s>>>(a, total);
+    else attn_small_kernel<128><<<(total + 1) / 2, 64, 0, s>>>(a, total);
   } else {
     dim3 grid(((a.S + 63) / 64) * a.num_seq, a.heads);
-    if (a.dh == 64) attn_flash_kernel<64><<<grid, 128, 0, s>>>(a);
-    else attn_flash_kernel<32><<<grid, 128, 0, s>>>(a);
+    const size_t smem = static_cast<size_t>(64 + 4 * 64) * DHT * 2 + 2 * 64 * sizeof(float);   // sQ | sK[2] | sV[2] | sFlag[2]
+    if (DHT == 64) attn_flash_kernel<64><<<grid, 128, smem, s>>>(a);
+    else if (DHT == 32) attn_flash_kernel<32><<<grid, 128, smem, s>>>(a);
+    else {
+      static bool attr_done = false;
+      if (!attr_done) {
+        const cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+      }
+      attn_flash_kernel<128><<<grid, 128, smem, s>>>(a);
+    }
   }
   return cudaGetLastError();
 }

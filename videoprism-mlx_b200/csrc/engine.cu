@@ -681,7 +681,7 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
   if (cfg->kind != VP_KIND_ENCODER && cfg->kind != VP_KIND_CLIP && cfg->kind != VP_KIND_CLASSIFIER) { g_create_error = "unknown model kind"; return VP_ERR_INVALID; }
   if (cfg->kind == VP_KIND_CLASSIFIER && cfg->num_classes <= 0) { g_create_error = "num_classes must be positive for a classifier"; return VP_ERR_INVALID; }
   const int dh = cfg->model_dim / cfg->num_heads;
-  if (dh != 64 && dh != 32) { g_create_error = "dim_per_head must be 32 or 64"; return VP_ERR_UNSUPPORTED; }
+  if (dh % 8 || dh > 128) { g_create_error = "dim_per_head must be a multiple of 8, at most 128"; return VP_ERR_UNSUPPORTED; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {

@@ -41,12 +41,18 @@ CHECKPOINTS = {
     "videoprism_lvt_public_v1_large": ("google/videoprism-lvt-large-f8r288", "flax_lvt_large_f8r288_repeated.npz"),
 }
 
-# models.py:82-161 (the configurations that have a MODELS entry)
+# models.py:82-161.  The giant configurations have no MODELS entry and no released checkpoint; the encoder / classifier run
+# (dim_per_head = 88 goes through the generic attention kernels), the video-text giant needs norm_policy 'primer_hybrid'.
 CONFIGS = {
     "videoprism_v1_base": dict(patch_size=18, pos_emb_shape=(16, 16, 16), model_dim=768, num_spatial_layers=12,
                                num_temporal_layers=4, num_heads=12, mlp_dim=3072, atten_logit_cap=50.0, scan=True),
     "videoprism_v1_large": dict(patch_size=18, pos_emb_shape=(8, 16, 16), model_dim=1024, num_spatial_layers=24,
                                 num_temporal_layers=4, num_heads=16, mlp_dim=4096, atten_logit_cap=50.0, scan=True),
+    "videoprism_v1_giant": dict(patch_size=18, pos_emb_shape=(8, 16, 16), model_dim=1408, num_spatial_layers=40,
+                                num_temporal_layers=4, num_heads=16, mlp_dim=6144, atten_logit_cap=50.0, scan=True),
+    "videoprism_lvt_v1_giant": dict(patch_size=18, pos_emb_shape=(8, 16, 16), num_spatial_layers=40, num_temporal_layers=4,
+                                    mlp_dim=6144, num_auxiliary_layers=2, enable_causal_atten=True, num_unimodal_layers=16,
+                                    norm_policy="primer_hybrid", model_dim=1408, num_heads=16, atten_logit_cap=50.0, scan=True),
     "videoprism_lvt_v1_base": dict(patch_size=18, pos_emb_shape=(16, 16, 16), num_spatial_layers=12, num_temporal_layers=4,
                                    mlp_dim=3072, num_auxiliary_layers=2, enable_causal_atten=True, num_unimodal_layers=12,
                                    norm_policy="pre", model_dim=768, num_heads=12, atten_logit_cap=50.0, scan=True),
@@ -387,6 +393,24 @@ def videoprism_v1_base():
 
 def videoprism_v1_large():
     return FactorizedEncoder(**CONFIGS["videoprism_v1_large"])
+
+
+def videoprism_v1_giant():
+    """models.py:174-176."""
+    return FactorizedEncoder(**CONFIGS["videoprism_v1_giant"])
+
+
+def videoprism_lvt_v1_giant(text_tokenizer: str = "c4_en"):
+    """models.py:193-197.  Constructible as in the reference; running it raises NotImplementedError (norm_policy
+    'primer_hybrid' is not implemented: no checkpoint of this model was released)."""
+    config = dict(CONFIGS["videoprism_lvt_v1_giant"])
+    config["vocabulary_size"] = TEXT_TOKENIZERS[text_tokenizer]["vocab_size"]
+    return FactorizedVideoCLIP(**config)
+
+
+def videoprism_vc_v1_giant(num_classes: int):
+    """models.py:216-221."""
+    return FactorizedVideoClassifier(encoder_params=CONFIGS["videoprism_v1_giant"], num_classes=num_classes)
 
 
 def videoprism_lvt_v1_base(text_tokenizer: str = "c4_en"):
