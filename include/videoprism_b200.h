@@ -62,6 +62,9 @@ typedef struct vp_config {
   int num_unimodal_layers;  /* CLIP only */
   int vocabulary_size;      /* CLIP only */
   int num_classes;          /* classifier only (videoprism/models.py:200-221) */
+  int text_norm_policy;     /* CLIP text tower only: 0 = 'pre' (base / large), 1 = 'primer_hybrid' (giant, videoprism/models.py:155;
+                               videoprism/layers.py:819-820,:846-847,:388-389,:414-415).  The vision stacks are always 'pre'
+                               (videoprism/encoders.py:832,:853) */
 } vp_config;
 
 /* -- lifecycle: replaces models.get_model (videoprism/models.py:268-303) and

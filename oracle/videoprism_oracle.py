@@ -72,9 +72,21 @@ def tiny_config(kind: str = "encoder", **over) -> dict:
 # "repeated" = nn.scan-stacked leading [L] axis, layers.py:925-936,
 # convert_weights.py:188-198; '/'-joined keys utils.py:84-105)
 # ----------------------------------------------------------------------------
-def _stack_specs(prefix: str, L: int, D: int, H: int, F: int) -> List[Tuple[str, tuple, str]]:
+def _stack_specs(prefix: str, L: int, D: int, H: int, F: int, norm_policy: str = "pre") -> List[Tuple[str, tuple, str]]:
     dh = D // H
     p = prefix + "/x_layers"
+    if norm_policy == "primer_hybrid":
+        base = _stack_specs(prefix, L, D, H, F)
+        out = []
+        for key, shape, kind in base:
+            if "/layer_norm/" in key:
+                out.append((key.replace("/layer_norm/", "/pre_layer_norm/"), shape, kind))
+                if key.endswith("/bias"):   # after the pre_layer_norm pair of this sub-layer
+                    out.append((key.replace("/layer_norm/bias", "/post_layer_norm/scale"), shape, "ln_scale"))
+                    out.append((key.replace("/layer_norm/bias", "/post_layer_norm/bias"), shape, "bias"))
+            else:
+                out.append((key, shape, kind))
+        return out
     return [
         (p + "/layer_norm/scale", (L, D), "ln_scale"),
         (p + "/layer_norm/bias", (L, D), "bias"),
@@ -157,7 +169,7 @@ def param_specs(cfg: dict) -> List[Tuple[str, tuple, str]]:
         (tp + "/cls_emb", (1, 1, D), "matrix"),
     ]
     # text tower: mlp_dim = 4*model_dim (encoders.py:897)
-    s += _stack_specs(tp + "/unimodal_transformer", cfg["num_unimodal_layers"], D, H, 4 * D)
+    s += _stack_specs(tp + "/unimodal_transformer", cfg["num_unimodal_layers"], D, H, 4 * D, cfg.get("norm_policy", "pre"))
     s += [
         (tp + "/unimodal_ln/scale", (D,), "ln_scale"),
         (tp + "/unimodal_ln/bias", (D,), "bias"),
@@ -296,21 +308,30 @@ def attention_layer(xq, xkv, p: dict, mask, cap: float, per_dim_scale=None, hidd
 
 
 def transformer_block(x, p: dict, mask, paddings, cap: float, act) -> torch.Tensor:
-    """layers.py:797-872 (norm_policy 'pre') + TransformerFeedForward :371-430."""
-    n = layer_norm(x, p["layer_norm/scale"], p["layer_norm/bias"])
+    """layers.py:797-872 + TransformerFeedForward :371-430, norm_policy 'pre' (every released model) or 'primer_hybrid'
+    (the giant video-text model's text tower, models.py:155), told apart by the parameter names as the reference names
+    them ('layer_norm' vs 'pre_layer_norm' + 'post_layer_norm', layers.py:819-822,:846-849,:388-391,:414-417)."""
+    primer = "pre_layer_norm/scale" in p
+    pre = "pre_layer_norm" if primer else "layer_norm"
+    n = layer_norm(x, p[pre + "/scale"], p[pre + "/bias"])
     att = {k[len("self_attention/"):]: v for k, v in p.items() if k.startswith("self_attention/")}
-    y = x + attention_layer(n, n, att, mask, cap)                     # :827-855
-    m = layer_norm(y, p["ff_layer/layer_norm/scale"], p["ff_layer/layer_norm/bias"])   # :391
+    a = attention_layer(n, n, att, mask, cap)                         # :827-844
+    if primer:
+        a = layer_norm(a, p["post_layer_norm/scale"], p["post_layer_norm/bias"])       # :846-847
+    y = x + a                                                         # :855
+    m = layer_norm(y, p["ff_layer/" + pre + "/scale"], p["ff_layer/" + pre + "/bias"])   # :388-391
     keep = (1.0 - paddings)[..., None]
     u = act(m @ p["ff_layer/ffn_layer1/linear/kernel"] + p["ff_layer/ffn_layer1/linear/bias"]) * keep   # :394-398
     w = (u @ p["ff_layer/ffn_layer2/linear/kernel"] + p["ff_layer/ffn_layer2/linear/bias"]) * keep      # :405-411
+    if primer:
+        w = layer_norm(w, p["ff_layer/post_layer_norm/scale"], p["ff_layer/post_layer_norm/bias"])     # :414-415
     return y + w                                                      # :425
 
 
 def stacked_transformer(x, stack: dict, paddings, cap: float, act, causal: bool) -> torch.Tensor:
     """layers.py:989-1041 with the nn.scan over the leading [L] axis (:875-937)."""
     mask = attention_masks_for_fprop(x, paddings, causal)
-    L = stack["layer_norm/scale"].shape[0]
+    L = next(iter(stack.values())).shape[0]
     for l in range(L):
         x = transformer_block(x, {k: v[l] for k, v in stack.items()}, mask, paddings, cap, act)
     return x

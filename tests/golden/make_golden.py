@@ -88,6 +88,7 @@ def tiny_cases():
     save("clip_tiny", **arrays)
     classifier_case()
     giant_head_case()
+    primer_case()
 
 
 def giant_head_case():
@@ -102,6 +103,22 @@ def giant_head_case():
     outp, _ = m.apply(tree_of(W), jnp.asarray(v), train=False, frame_paddings=jnp.asarray(fp))
     save("enc_tiny_dh88", features=np.asarray(out), spatial_features=np.asarray(outs["spatial_features"]),
          features_frame_paddings=np.asarray(outp), frame_paddings=fp)
+
+
+def primer_case():
+    # the giant video-text configuration (models.py:146-161): text tower with norm_policy 'primer_hybrid'
+    # (pre_layer_norm + post_layer_norm around attention and FFN); vision / auxiliary stacks stay 'pre'
+    cfg = O.tiny_config("clip", norm_policy="primer_hybrid")
+    W = O.make_synthetic_weights(cfg)
+    v = O.make_video(2, 4, 16, seed=16, kind="normal")
+    ids, pad = O.make_text(5, vocab=cfg["vocabulary_size"], max_len=8)
+    pad[:, 4:] = (np.arange(4)[None, :] >= np.array([0, 1, 2, 3, 4])[:, None]).astype(np.float32)
+    ids = np.where(pad > 0, 0, ids).astype(np.int32)
+    m = encoders.FactorizedVideoCLIP(scan=True, enable_causal_atten=True, **{k: x for k, x in cfg.items() if k != "kind"})
+    ve, te, _ = m.apply(tree_of(W), jnp.asarray(v), jnp.asarray(ids), jnp.asarray(pad), train=False)
+    ve_raw, te_raw, _ = m.apply(tree_of(W), jnp.asarray(v), jnp.asarray(ids), jnp.asarray(pad), train=False, normalize=False)
+    save("clip_tiny_primer", ids=ids, paddings=pad, video_emb=np.asarray(ve), text_emb=np.asarray(te),
+         video_emb_raw=np.asarray(ve_raw), text_emb_raw=np.asarray(te_raw))
 
 
 def classifier_case():
@@ -150,6 +167,9 @@ def full_size_cases():
 if __name__ == "__main__":
     if "--classifier-only" in sys.argv:
         classifier_case()
+        sys.exit(0)
+    if "--primer-only" in sys.argv:
+        primer_case()
         sys.exit(0)
     if "--dh88-only" in sys.argv:
         giant_head_case()

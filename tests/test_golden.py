@@ -66,6 +66,24 @@ def test_tiny_encoder_giant_head_width():
     assert np.abs(outp - g["features_frame_paddings"]).max() <= FEAT_TOL
 
 
+def test_tiny_clip_primer_hybrid_text_tower():
+    """norm_policy 'primer_hybrid' (the giant video-text configuration, models.py:146-161): only the text tower changes
+    (encoders.py:899); 8 more leaves than the 'pre' model (88, encoders_test.py:340)."""
+    g = load("clip_tiny_primer")
+    cfg = O.tiny_config("clip", norm_policy="primer_hybrid")
+    W = O.make_synthetic_weights(cfg)
+    assert len(W) == 88 + 4
+    v = O.make_video(2, 4, 16, seed=16, kind="normal")
+    ve, te, _ = O.run_clip(cfg, W, v, g["ids"], g["paddings"])
+    assert np.abs(ve - g["video_emb"]).max() <= EMB_TOL and np.abs(te - g["text_emb"]).max() <= EMB_TOL
+    ve, te, _ = O.run_clip(cfg, W, v, g["ids"], g["paddings"], normalize=False)
+    assert np.abs(ve - g["video_emb_raw"]).max() <= FEAT_TOL and np.abs(te - g["text_emb_raw"]).max() <= FEAT_TOL
+    # and it is not the 'pre' model under another name
+    cfg0 = O.tiny_config("clip")
+    _, te0, _ = O.run_clip(cfg0, O.make_synthetic_weights(cfg0), None, g["ids"], g["paddings"])
+    assert np.abs(te0 - g["text_emb"]).max() > 1e-2
+
+
 def test_tiny_classifier():
     """encoders_test.py:183-231 shapes: FactorizedVideoClassifier through the reference's own code."""
     g = load("classifier_tiny")

@@ -129,3 +129,22 @@ def test_tiny_encoder_giant_head_width():
     check("  spatial_features", outs["spatial_features"], g["spatial_features"])
     outp, _ = m.apply(W, v, train=False, frame_paddings=g["frame_paddings"])
     check("  with frame_paddings", outp, g["features_frame_paddings"])
+
+
+@pytest.mark.parametrize("fuse_ln", ["1", "0"])
+def test_tiny_clip_primer_hybrid_text_tower(fuse_ln, monkeypatch):
+    """Text tower with norm_policy 'primer_hybrid' (models.py:146-161 giant video-text configuration) against the golden
+    made by the reference's own code; with the pre-LayerNorms folded into the GEMMs (default) and standalone."""
+    import videoprism_b200 as vp
+    monkeypatch.setenv("VP_FUSE_LN", fuse_ln)
+    g = np.load(os.path.join(G, "clip_tiny_primer.npz"))
+    cfg = O.tiny_config("clip", norm_policy="primer_hybrid")
+    W = O.make_synthetic_weights(cfg)
+    m = model_for(cfg)
+    assert list(vp.synthetic_state(m, seed=1234)) == list(W)          # same leaves, same order as the oracle's tree
+    v = O.make_video(2, 4, 16, seed=16, kind="normal")
+    ve, te, _ = m.apply(W, v, g["ids"], g["paddings"], train=False)
+    check("primer clip video_emb", ve, g["video_emb"])
+    check("primer clip text_emb", te, g["text_emb"])
+    _, te_raw, _ = m.apply(W, None, g["ids"], g["paddings"], train=False, normalize=False)
+    check("primer clip text_emb (raw)", te_raw, g["text_emb_raw"])

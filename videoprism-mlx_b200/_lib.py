@@ -19,7 +19,7 @@ class VpConfig(C.Structure):
         ("model_dim", C.c_int), ("num_spatial_layers", C.c_int), ("num_temporal_layers", C.c_int),
         ("num_heads", C.c_int), ("mlp_dim", C.c_int), ("atten_logit_cap", C.c_float),
         ("num_auxiliary_layers", C.c_int), ("num_unimodal_layers", C.c_int), ("vocabulary_size", C.c_int),
-        ("num_classes", C.c_int),
+        ("num_classes", C.c_int), ("text_norm_policy", C.c_int),
     ]
 
 

@@ -114,6 +114,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
             y[0] += t0.x; y[1] += t0.y; y[2] += t0.z; y[3] += t0.w;
             y[4] += t1.x; y[5] += t1.y; y[6] += t1.z; y[7] += t1.w;
           }
+          if (a.resid != nullptr) {
+            const uint4 r = *reinterpret_cast<const uint4*>(a.resid + static_cast<size_t>(row) * a.ldr + c);
+            y[0] += bf16_lo(r.x); y[1] += bf16_hi(r.x); y[2] += bf16_lo(r.y); y[3] += bf16_hi(r.y);
+            y[4] += bf16_lo(r.z); y[5] += bf16_hi(r.z); y[6] += bf16_lo(r.w); y[7] += bf16_hi(r.w);
+          }
           uint4 o;
           o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
           o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
@@ -293,7 +298,7 @@ __global__ void text_embed_kernel(const int32_t* __restrict__ ids, const float* 
 
 cudaError_t launch_layernorm(cudaStream_t s, const LnArgs& a) {
   if (a.M <= 0) return cudaSuccess;
-  if ((a.D % 8) || (a.ldx % 8) || a.D > 8 * 32 * 6) return cudaErrorInvalidValue;
+  if ((a.D % 8) || (a.ldx % 8) || a.D > 8 * 32 * 6 || (a.resid != nullptr && (a.ldr % 8))) return cudaErrorInvalidValue;
   const int warps = 8;
   const int full = (a.M + warps - 1) / warps;
   const int cap = num_sms() * 8;                       // persistent: up to 8 blocks of 8 warps per SM

@@ -65,6 +65,10 @@ struct StackWeights {
   bf16 *wqkv_ln = nullptr, *w1_ln = nullptr;
   float *c1_qkv = nullptr, *c2_qkv = nullptr, *c1_ffn1 = nullptr, *c2_ffn1 = nullptr;
   float *f_wqkv = nullptr, *f_bqkv = nullptr, *f_w1 = nullptr, *f_b1 = nullptr;   // fp32 [L][3][D][D], [L][3][D], [L][D][F], [L][F] (unscaled)
+  // norm_policy 'primer_hybrid' (layers.py:819-820,:846-847,:388-389,:414-415): ln1 / ln2 are the 'pre_layer_norm's and the
+  // attention / FFN outputs pass through these 'post_layer_norm's before the residual add
+  bool primer = false;
+  float *lnp1_g = nullptr, *lnp1_b = nullptr, *lnp2_g = nullptr, *lnp2_b = nullptr;
 };
 
 struct ParamSpec {
@@ -171,8 +175,8 @@ cudaError_t copy_f32(const float* src, float* dst, size_t n, cudaStream_t s) {
 }
 
 // Parameter tree of one scan-stacked Transformer stack (layers.py:797-872).
-cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, int L, int D, int H, int F) {
-  w->L = L; w->D = D; w->H = H; w->F = F;
+cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, int L, int D, int H, int F, bool primer = false) {
+  w->L = L; w->D = D; w->H = H; w->F = F; w->primer = primer;
   const int dh = D / H;
   cudaError_t e;
   if ((e = dev_alloc(h, &w->wqkv, (size_t)L * 3 * D * D)) != cudaSuccess) return e;
@@ -199,15 +203,28 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
   if ((e = dev_alloc(h, &w->f_bqkv, (size_t)L * 3 * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &w->f_w1, (size_t)L * D * F)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &w->f_b1, (size_t)L * F)) != cudaSuccess) return e;
+  if (primer) {
+    if ((e = dev_alloc(h, &w->lnp1_g, (size_t)L * D)) != cudaSuccess) return e;
+    if ((e = dev_alloc(h, &w->lnp1_b, (size_t)L * D)) != cudaSuccess) return e;
+    if ((e = dev_alloc(h, &w->lnp2_g, (size_t)L * D)) != cudaSuccess) return e;
+    if ((e = dev_alloc(h, &w->lnp2_b, (size_t)L * D)) != cudaSuccess) return e;
+  }
   h->stacks.push_back(w);
   const std::string p = prefix + "/x_layers";
+  const std::string pre = primer ? "pre_layer_norm" : "layer_norm";
   // query scale dh^-0.5 (layers.py:569-584, internal_enable_per_dim_scale=False) is folded into Wq, bq.
   const float qscale = 1.0f / sqrtf(static_cast<float>(dh));
   StackWeights ww = *w;
-  add_spec(h, p + "/layer_norm/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+  add_spec(h, p + "/" + pre + "/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return vp::launch_affine_f32(st, s, ww.ln1_g, (size_t)L * D, 1.0f, 1.0f); });
-  add_spec(h, p + "/layer_norm/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+  add_spec(h, p + "/" + pre + "/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return copy_f32(s, ww.ln1_b, (size_t)L * D, st); });
+  if (primer) {
+    add_spec(h, p + "/post_layer_norm/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+      return vp::launch_affine_f32(st, s, ww.lnp1_g, (size_t)L * D, 1.0f, 1.0f); });
+    add_spec(h, p + "/post_layer_norm/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+      return copy_f32(s, ww.lnp1_b, (size_t)L * D, st); });
+  }
   const char* names[3] = {"query", "key", "value"};
   for (int i = 0; i < 3; ++i) {
     const float sc = (i == 0) ? qscale : 1.0f;
@@ -238,10 +255,16 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
     return vp::launch_cast_bf16(st, s, ww.wo, (size_t)L * D * D, 1.0f); });
   add_spec(h, p + "/self_attention/post/b", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return copy_f32(s, ww.bo, (size_t)L * D, st); });
-  add_spec(h, p + "/ff_layer/layer_norm/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+  add_spec(h, p + "/ff_layer/" + pre + "/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return vp::launch_affine_f32(st, s, ww.ln2_g, (size_t)L * D, 1.0f, 1.0f); });
-  add_spec(h, p + "/ff_layer/layer_norm/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+  add_spec(h, p + "/ff_layer/" + pre + "/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return copy_f32(s, ww.ln2_b, (size_t)L * D, st); });
+  if (primer) {
+    add_spec(h, p + "/ff_layer/post_layer_norm/scale", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+      return vp::launch_affine_f32(st, s, ww.lnp2_g, (size_t)L * D, 1.0f, 1.0f); });
+    add_spec(h, p + "/ff_layer/post_layer_norm/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
+      return copy_f32(s, ww.lnp2_b, (size_t)L * D, st); });
+  }
   add_spec(h, p + "/ff_layer/ffn_layer1/linear/kernel", {L, D, F}, [ww, L, D, F](const float* s, cudaStream_t st) {
     for (int l = 0; l < L; ++l) {
       cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * D * F, ww.w1 + (size_t)l * F * D, D, F, D, 1.0f);
@@ -351,7 +374,7 @@ cudaError_t add_clip_extras(vp_handle* h) {
   add_spec(h, tp + "/token_emb/emb_var", {c.vocabulary_size, D}, [hh, D](const float* s, cudaStream_t st) {
     return copy_f32(s, hh->tok_emb, (size_t)hh->cfg.vocabulary_size * D, st); });
   add_spec(h, tp + "/cls_emb", {1, 1, D}, [hh, D](const float* s, cudaStream_t st) { return copy_f32(s, hh->cls_emb, D, st); });
-  if ((e = add_stack(h, tp + "/unimodal_transformer", &h->text, c.num_unimodal_layers, D, H, 4 * D)) != cudaSuccess) return e;
+  if ((e = add_stack(h, tp + "/unimodal_transformer", &h->text, c.num_unimodal_layers, D, H, 4 * D, c.text_norm_policy == 1)) != cudaSuccess) return e;
   if ((e = add_ln(h, tp + "/unimodal_ln", &h->uni_ln_g, &h->uni_ln_b, D)) != cudaSuccess) return e;
   return cudaSuccess;
 }
@@ -534,7 +557,7 @@ int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayo
     ln.x = x; ln.ldx = D; ln.y_bf16 = n; ln.M = M; ln.D = D;
     vp::GemmEpilogue e1;
     if (fuse) {
-      e1.bias = w.c2_qkv + (size_t)l * 3 * D; e1.ln_stats_in = stats_a; e1.ln_slots = (l == 0) ? slots_a : gslots;
+      e1.bias = w.c2_qkv + (size_t)l * 3 * D; e1.ln_stats_in = stats_a; e1.ln_slots = (l == 0) ? slots_a : (w.primer ? 1 : gslots);
       e1.ln_colsum = w.c1_qkv + (size_t)l * 3 * D; e1.ln_dim = D;
       CK(vp::launch_gemm(st, x, D, w.wqkv_ln + (size_t)l * 3 * D * D, D, qkv, 3 * D, M, 3 * D, D, e1)); h->mark(st, tag[1]);
     } else {
@@ -552,13 +575,24 @@ int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayo
     CK(vp::launch_attention(st, at)); h->mark(st, tag[2]);
     h->launches += n_attn - 1;
     vp::GemmEpilogue e2;
-    e2.bias = w.bo + (size_t)l * D; e2.resid = x; e2.ldr = D;
-    if (fuse) e2.stats_out = stats_b;
-    CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, x, D, M, D, D, e2)); h->mark(st, tag[3]);
+    e2.bias = w.bo + (size_t)l * D;
+    if (w.primer) {
+      // 'primer_hybrid': x += post_layer_norm(attention output) (layers.py:846-855); the projection lands in the (idle)
+      // FFN hidden buffer, the LayerNorm kernel adds the residual and emits the row statistics for the folded FFN1
+      CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, u, D, M, D, D, e2)); h->mark(st, tag[3]);
+      vp::LnArgs lp;
+      lp.x = u; lp.ldx = D; lp.gamma1 = w.lnp1_g + (size_t)l * D; lp.beta = w.lnp1_b + (size_t)l * D; lp.y_bf16 = x;
+      lp.resid = x; lp.ldr = D; lp.M = M; lp.D = D; lp.stats_out = fuse ? stats_b : nullptr;
+      CK(vp::launch_layernorm(st, lp)); h->mark(st, tag[0]);
+    } else {
+      e2.resid = x; e2.ldr = D;
+      if (fuse) e2.stats_out = stats_b;
+      CK(vp::launch_gemm(st, n, D, w.wo + (size_t)l * D * D, D, x, D, M, D, D, e2)); h->mark(st, tag[3]);
+    }
     vp::GemmEpilogue e3;
     e3.act = act; e3.row_scale = sl.row_scale;
     if (fuse) {
-      e3.bias = w.c2_ffn1 + (size_t)l * F; e3.ln_stats_in = stats_b; e3.ln_slots = gslots;
+      e3.bias = w.c2_ffn1 + (size_t)l * F; e3.ln_stats_in = stats_b; e3.ln_slots = w.primer ? 1 : gslots;
       e3.ln_colsum = w.c1_ffn1 + (size_t)l * F; e3.ln_dim = D;
       CK(vp::launch_gemm(st, x, D, w.w1_ln + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->mark(st, tag[4]);
     } else {
@@ -568,9 +602,18 @@ int run_stack(vp_handle* h, const StackWeights& w, bf16* x, int M, const SeqLayo
       CK(vp::launch_gemm(st, n, D, w.w1 + (size_t)l * F * D, D, u, F, M, F, D, e3)); h->mark(st, tag[4]);
     }
     vp::GemmEpilogue e4;
-    e4.bias = w.b2 + (size_t)l * D; e4.row_scale = sl.row_scale; e4.resid = x; e4.ldr = D;
-    if (fuse) e4.stats_out = stats_a;
-    CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, x, D, M, D, F, e4)); h->mark(st, tag[5]);
+    e4.bias = w.b2 + (size_t)l * D; e4.row_scale = sl.row_scale;
+    if (w.primer) {   // x += post_layer_norm(FFN output, zeroed on padded tokens) (layers.py:410-424)
+      CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, n, D, M, D, F, e4)); h->mark(st, tag[5]);
+      vp::LnArgs lp;
+      lp.x = n; lp.ldx = D; lp.gamma1 = w.lnp2_g + (size_t)l * D; lp.beta = w.lnp2_b + (size_t)l * D; lp.y_bf16 = x;
+      lp.resid = x; lp.ldr = D; lp.M = M; lp.D = D; lp.stats_out = fuse ? stats_a : nullptr;
+      CK(vp::launch_layernorm(st, lp)); h->mark(st, tag[0]);
+    } else {
+      e4.resid = x; e4.ldr = D;
+      if (fuse) e4.stats_out = stats_a;
+      CK(vp::launch_gemm(st, u, F, w.w2 + (size_t)l * D * F, F, x, D, M, D, F, e4)); h->mark(st, tag[5]);
+    }
   }
   return VP_OK;
 }
@@ -679,6 +722,7 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
     return VP_ERR_INVALID;
   }
   if (cfg->kind != VP_KIND_ENCODER && cfg->kind != VP_KIND_CLIP && cfg->kind != VP_KIND_CLASSIFIER) { g_create_error = "unknown model kind"; return VP_ERR_INVALID; }
+  if (cfg->text_norm_policy != 0 && cfg->text_norm_policy != 1) { g_create_error = "text_norm_policy must be 0 ('pre') or 1 ('primer_hybrid')"; return VP_ERR_UNSUPPORTED; }
   if (cfg->kind == VP_KIND_CLASSIFIER && cfg->num_classes <= 0) { g_create_error = "num_classes must be positive for a classifier"; return VP_ERR_INVALID; }
   const int dh = cfg->model_dim / cfg->num_heads;
   if (dh % 8 || dh > 128) { g_create_error = "dim_per_head must be a multiple of 8, at most 128"; return VP_ERR_UNSUPPORTED; }

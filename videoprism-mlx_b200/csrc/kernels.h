@@ -54,6 +54,7 @@ struct LnArgs {
   float* y_f32 = nullptr;         // [M, D] or null (LN(x) without the table add)
   float* stats_out = nullptr;     // [M][1][2] (sum, sum of squares) of the stored bf16 rows y_bf16 (one slot), or null
   const float* add_table = nullptr; int add_div = 1; int add_mod = 1;   // temporal pos-emb, encoders.py:553
+  const bf16* resid = nullptr; int ldr = 0;   // y_bf16 = LN(x) + resid (norm_policy 'primer_hybrid', layers.py:846-855); may alias y_bf16
   int M = 0, D = 0;
 };
 cudaError_t launch_layernorm(cudaStream_t s, const LnArgs& a);

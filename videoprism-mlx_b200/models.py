@@ -116,12 +116,16 @@ class _Module:
             num_spatial_layers=c["num_spatial_layers"], num_temporal_layers=c["num_temporal_layers"], num_heads=c["num_heads"],
             mlp_dim=c["mlp_dim"], atten_logit_cap=float(c.get("atten_logit_cap", 0.0)),
             num_auxiliary_layers=int(c.get("num_auxiliary_layers", 0)), num_unimodal_layers=int(c.get("num_unimodal_layers", 0)),
-            vocabulary_size=int(c.get("vocabulary_size", 0)), num_classes=int(c.get("num_classes", 0)))
+            vocabulary_size=int(c.get("vocabulary_size", 0)), num_classes=int(c.get("num_classes", 0)),
+            text_norm_policy={"pre": 0, "primer_hybrid": 1}[c.get("norm_policy", "pre")] if self._kind == _lib.VP_KIND_CLIP else 0)
 
     def _ensure_handle(self):
         if self._handle is None:
-            if self.config.get("norm_policy", "pre") != "pre":
-                raise NotImplementedError("only norm_policy='pre' (all released configs) is implemented")
+            policy = self.config.get("norm_policy", "pre")
+            # the video-text model hands norm_policy to its TEXT tower only (encoders.py:899; vision stacks: 'pre', :832,:853)
+            allowed = ("pre", "primer_hybrid") if self._kind == _lib.VP_KIND_CLIP else ("pre",)
+            if policy not in allowed:
+                raise NotImplementedError(f"norm_policy={policy!r} is not implemented (supported here: {allowed})")
             lib = _lib.lib()
             cfg = self._vp_config()
             h = C.c_void_p()
@@ -401,8 +405,7 @@ def videoprism_v1_giant():
 
 
 def videoprism_lvt_v1_giant(text_tokenizer: str = "c4_en"):
-    """models.py:193-197.  Constructible as in the reference; running it raises NotImplementedError (norm_policy
-    'primer_hybrid' is not implemented: no checkpoint of this model was released)."""
+    """models.py:193-197 (text tower with norm_policy 'primer_hybrid', 16 blocks; no checkpoint was released)."""
     config = dict(CONFIGS["videoprism_lvt_v1_giant"])
     config["vocabulary_size"] = TEXT_TOKENIZERS[text_tokenizer]["vocab_size"]
     return FactorizedVideoCLIP(**config)
