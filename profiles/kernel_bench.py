@@ -150,5 +150,5 @@ dst = torch.empty((8 * 16, 288, 288, 3), dtype=torch.uint8, device="cuda")
 def f_ingest():
     assert lib.vp_resize_frames_u8(fr.data_ptr(), 8 * 16, 360, 640, dst.data_ptr(), 288, 0, st) == 0
 ms = timeit(f_ingest)
-algo = 8 * 16 * (360 * 450 * 3 + 288 * 288 * 3)   # the cropped source window (360 x 450) + the output
+algo = 8 * 16 * (360 * 360 * 3 + 288 * 288 * 3)   # the cropped source window (360 rows x 360 columns: x in [140, 500)) + the output
 print(f"frame ingest 8x16x360x640 -> 288^2: {ms*1e3:8.1f} us  {algo / ms / 1e6:7.0f} GB/s algorithmic")
