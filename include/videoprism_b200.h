@@ -69,7 +69,12 @@ typedef struct vp_config {
 
 /* -- lifecycle: replaces models.get_model (videoprism/models.py:268-303) and
  *    models_mlx.load_video_encoder / load_model (videoprism/models_mlx.py:91-210) -------------- */
-VP_API int vp_create(const vp_config* cfg, vp_handle** out);
+VP_API int vp_create(const vp_config* cfg, vp_handle** out);   /* on the calling thread's current CUDA device */
+/* Same on an explicit device ordinal (device < 0: the current device).  Frameworks that select devices lazily (PyTorch
+ * does not call cudaSetDevice for a device without a context yet) should use this one: the handle, its weights, its
+ * workspace and every kernel it launches live on `device`; all buffers passed to its entry points must too. */
+VP_API int vp_create_on_device(const vp_config* cfg, int device, vp_handle** out);
+VP_API int vp_handle_device(const vp_handle* h);                /* device ordinal the handle is bound to */
 VP_API void vp_destroy(vp_handle* h);
 VP_API const char* vp_last_error(const vp_handle* h); /* h may be NULL: last error of a failed vp_create */
 

@@ -375,3 +375,37 @@ def test_fprop_dtype_bfloat16_returns_bf16_features():
     assert torch.equal(b16, f32.to(torch.bfloat16))
     host, _ = m16.apply(W, v.cpu().numpy(), train=False)      # numpy callers keep float32
     assert host.dtype == np.float32 and np.array_equal(host, f32.cpu().numpy())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices():
+    """A handle is bound to the device that is current when it is created (include/videoprism_b200.h); one process may
+    hold handles on several GPUs.  Kernel attributes (dynamic shared memory opt-in) are per device: the second device must
+    run the >48 KB kernels too, and give bitwise the same features."""
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    W = O.make_synthetic_weights(cfg)
+    v = torch.from_numpy(O.make_video(2, 16, 288, seed=31))
+    outs = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            m = vp.get_model("videoprism_public_v1_base")
+            m.load_state(W)
+            o, _ = m(v.cuda(dev))
+            torch.cuda.synchronize(dev)
+            outs.append(o.cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert m.device_index == 1
+    with pytest.raises(ValueError, match="lives on cuda:1"):
+        m(v.cuda(0))
+    # video-text model on the second device: long-sequence attention, pooler, text tower
+    cfgc = O.tiny_config("clip")
+    Wc = O.make_synthetic_weights(cfgc)
+    ids, pad = O.make_text(3, vocab=cfgc["vocabulary_size"], max_len=8)
+    vt = O.make_video(2, 4, 16, seed=32, kind="normal")
+    res = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            m = make_model(cfgc)
+            res.append(m.apply(Wc, vt, ids, pad, train=False)[:2])
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])

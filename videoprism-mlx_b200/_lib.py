@@ -27,6 +27,8 @@ _P = C.c_void_p
 _I = C.c_int
 _PROTOS = {
     "vp_create": (_I, [C.POINTER(VpConfig), C.POINTER(_P)]),
+    "vp_create_on_device": (_I, [C.POINTER(VpConfig), _I, C.POINTER(_P)]),
+    "vp_handle_device": (_I, [_P]),
     "vp_destroy": (None, [_P]),
     "vp_last_error": (C.c_char_p, [_P]),
     "vp_set_weight": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),

@@ -379,12 +379,9 @@ cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
     if (DHT == 64) attn_flash_kernel<64><<<grid, 128, smem, s>>>(a);
     else if (DHT == 32) attn_flash_kernel<32><<<grid, 128, smem, s>>>(a);
     else {
-      static bool attr_done = false;
-      if (!attr_done) {
-        const cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-      }
+      static int granted[kMaxDevices] = {};
+      const cudaError_t e = ensure_dynamic_smem(attn_flash_kernel<128>, static_cast<int>(smem), granted);
+      if (e != cudaSuccess) return e;
       attn_flash_kernel<128><<<grid, 128, smem, s>>>(a);
     }
   }

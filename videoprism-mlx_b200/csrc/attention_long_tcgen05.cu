@@ -374,11 +374,10 @@ cudaError_t launch_attention_long_tcgen05(cudaStream_t s, const AttnArgs& a) {
   p.range = 0.5f * a.cap;
   p.cap_l2 = a.cap * kLog2e;
   p.inv_cap = 1.0f / a.cap;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_long_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  static int granted[kMaxDevices] = {};
+  {
+    const cudaError_t e = ensure_dynamic_smem(attn_long_tcgen05_kernel, kSmemBytes, granted);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const int grid = p.num_problems < num_sms() ? p.num_problems : num_sms();
   cudaLaunchConfig_t cfg = {};

@@ -629,13 +629,28 @@ int ensure_workspace(vp_handle* h, size_t M, int D, int F) {
   return VP_OK;
 }
 
-int check_ready(vp_handle* h) {
+// Selects the handle's device for the duration of one C-ABI call and restores the caller's current device afterwards: an
+// entry point must not change the calling thread's device as a side effect (a destructor running vp_destroy for a model
+// on cuda:0 would otherwise silently move the caller off cuda:1).
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (dev >= 0 && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceScope() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
+int check_ready(vp_handle* h) {   // callers hold a DeviceScope on h->device
   if (h == nullptr) return VP_ERR_INVALID;
   if (!h->finalized) return h->fail(VP_ERR_INCOMPLETE, "vp_finalize has not been called");
   int dev = -1;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device) {
-    if (cudaSetDevice(h->device) != cudaSuccess) return h->fail(VP_ERR_CUDA, "cannot select device %d", h->device);
-  }
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device) return h->fail(VP_ERR_CUDA, "cannot select device %d", h->device);
   return VP_OK;
 }
 
@@ -713,7 +728,11 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
 // ===================================================================== C ABI
 extern "C" {
 
-int vp_create(const vp_config* cfg, vp_handle** out) {
+int vp_create(const vp_config* cfg, vp_handle** out) { return vp_create_on_device(cfg, -1, out); }
+
+int vp_handle_device(const vp_handle* h) { return h ? h->device : -1; }
+
+int vp_create_on_device(const vp_config* cfg, int device, vp_handle** out) {
   if (out == nullptr || cfg == nullptr) { g_create_error = "null argument"; return VP_ERR_INVALID; }
   *out = nullptr;
   if (cfg->model_dim <= 0 || cfg->num_heads <= 0 || cfg->model_dim % cfg->num_heads || cfg->patch_size <= 0 ||
@@ -732,11 +751,21 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
     g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
     return VP_ERR_CUDA;
   }
+  if (device >= ndev) { g_create_error = "device ordinal " + std::to_string(device) + " out of range (" + std::to_string(ndev) + " devices)"; return VP_ERR_INVALID; }
+  if (device < 0 && (e = cudaGetDevice(&device)) != cudaSuccess) {
+    g_create_error = std::string("cannot query the current device: ") + cudaGetErrorString(e);
+    return VP_ERR_CUDA;
+  }
+  DeviceScope device_scope(device);   // cudaSetDevice also creates the primary context if this is the device's first use
   vp_handle* h = new vp_handle();
   h->cfg = *cfg;
   if (const char* ev = getenv("VP_HOST_CHUNK_CLIPS")) h->host_chunk_clips = atoi(ev);   // tuning knob of the host pipeline
   if (const char* ev = getenv("VP_FUSE_LN")) h->fuse_ln = atoi(ev) != 0;
-  cudaGetDevice(&h->device);
+  if (cudaGetDevice(&h->device) != cudaSuccess || h->device != device) {
+    g_create_error = "cannot select device " + std::to_string(device);
+    delete h;
+    return VP_ERR_CUDA;
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, h->device);
   if (prop.major != 10) {
@@ -758,7 +787,7 @@ int vp_create(const vp_config* cfg, vp_handle** out) {
 
 void vp_destroy(vp_handle* h) {
   if (h == nullptr) return;
-  cudaSetDevice(h->device);
+  DeviceScope device_scope(h->device);
   for (void* p : h->owned) cudaFree(p);
   for (auto& t : h->trace) cudaEventDestroy(t.second);
 
@@ -788,7 +817,7 @@ int64_t vp_weight_dim(const vp_handle* h, int i, int axis) {
 
 int vp_set_weight(vp_handle* h, const char* key, const void* data, const int64_t* shape, int ndim) {
   if (h == nullptr || key == nullptr || data == nullptr || (ndim > 0 && shape == nullptr)) return VP_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceScope device_scope(h->device);
   auto it = h->spec_index.find(key);
   if (it == h->spec_index.end()) return h->fail(VP_ERR_KEY, "unknown parameter key '%s'", key);
   ParamSpec& sp = h->specs[it->second];
@@ -825,7 +854,7 @@ static int finalize_stack(vp_handle* h, StackWeights* w) {
 
 int vp_finalize(vp_handle* h) {
   if (h == nullptr) return VP_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceScope device_scope(h->device);
   for (const ParamSpec& s : h->specs)
     if (!s.set) return h->fail(VP_ERR_INCOMPLETE, "parameter '%s' was never set", s.key.c_str());
   for (StackWeights* w : h->stacks) {
@@ -843,6 +872,7 @@ int vp_finalize(vp_handle* h) {
 
 static int encoder_forward_dev(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
                                void* out_features, void* spatial_features, int out_dtype, void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
@@ -889,6 +919,7 @@ static int encoder_forward_host_impl(vp_handle* h, const void* video_v, int in_d
                                      const float* frame_paddings, float* out_features, float* spatial_features, void* stream) {
   const char* video = static_cast<const char*>(video_v);
   const size_t esz = in_dtype == VP_U8 ? 1 : sizeof(float);
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
@@ -988,6 +1019,7 @@ int vp_encoder_forward_host_u8(vp_handle* h, const uint8_t* video, int B, int T,
 int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
                           int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
                           float* frame_embeddings, void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
@@ -1023,6 +1055,7 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
 
 int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings, float* logits,
                           float* global_embeddings, float* spatial_features, float* spatiotemporal_features, void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (h->cfg.kind != VP_KIND_CLASSIFIER) return h->fail(VP_ERR_INVALID, "handle is not a video classifier");
@@ -1049,6 +1082,7 @@ int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H,
 
 int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize, float* text_emb,
                          void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
@@ -1084,6 +1118,7 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
 
 int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, int normalize, float* video_emb,
                                void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (video == nullptr || video_emb == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return h->fail(VP_ERR_INVALID, "bad argument");
@@ -1102,6 +1137,7 @@ int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, int T, i
 
 int vp_clip_text_forward_host(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
                               float* text_emb, void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
   if (ids == nullptr || paddings == nullptr || text_emb == nullptr || Q <= 0 || L <= 0) return h->fail(VP_ERR_INVALID, "bad argument");
@@ -1148,7 +1184,7 @@ int vp_trace(vp_handle* h, int enable) {
 
 int vp_trace_report(vp_handle* h, char* buf, int cap) {
   if (h == nullptr || buf == nullptr || cap <= 0) return VP_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceScope device_scope(h->device);
   CK(cudaDeviceSynchronize());
   std::vector<std::string> order;
   std::map<std::string, std::pair<int, double>> agg;

@@ -525,15 +525,17 @@ bool pdl_enabled() {
   return on;
 }
 
-static int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+int num_sms() {   // of the current device (cached per device ordinal)
+  static int cache[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return cache[dev];
 }
 
 namespace {
@@ -553,11 +555,10 @@ cudaError_t launch_gemm_t(cudaStream_t s, const Maps& m, const KParams& kp_in, i
   kp.nbuf = (nbuf_env == 2 && RESID && !OUT_F32 && BN == 256 && kp.K <= 1024) ? 2 : 1;
   kp.stages = Cfg<BN, CG>::stages(kp.ln_stats_in != nullptr, kp.nbuf);
   const int kSmem = Cfg<BN, CG>::smem_bytes(kp.ln_stats_in != nullptr, kp.nbuf);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  static int granted[kMaxDevices] = {};   // one per template instantiation
+  {
+    const cudaError_t e = ensure_dynamic_smem(kern, 232448, granted);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

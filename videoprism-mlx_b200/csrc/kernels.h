@@ -9,6 +9,22 @@ namespace vp {
 
 typedef __nv_bfloat16 bf16;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the (kernel, device) pair: a process that drives several
+// GPUs must set it on each of them.  `cache` is a per-call-site array, one slot per device ordinal, holding the largest
+// size already granted on that device; concurrent callers may both set the attribute, which is harmless.
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, int (&cache)[kMaxDevices]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool cached = dev >= 0 && dev < kMaxDevices;
+  if (cached && cache[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && cached) cache[dev] = bytes;
+  return e;
+}
+
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
 // Epilogue of C = A * W^T:  v = acc + bias[n]; v = act(v); v *= row_scale[m];

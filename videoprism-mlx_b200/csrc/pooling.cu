@@ -263,12 +263,8 @@ cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D
   cudaError_t e;
   {
     const size_t smem = static_cast<size_t>(H) * D * sizeof(float);
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-      e = cudaFuncSetAttribute(pool_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return e;
-      attr_set = smem;
-    }
+    static int granted[kMaxDevices] = {};
+    if (smem > 48 * 1024 && (e = ensure_dynamic_smem(pool_scores_kernel, static_cast<int>(smem), granted)) != cudaSuccess) return e;
     int grid = (rows + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
     pool_scores_kernel<<<grid, 256, smem, s>>>(x, wkq, scores, rows, D, H);

@@ -129,9 +129,28 @@ class _Module:
             lib = _lib.lib()
             cfg = self._vp_config()
             h = C.c_void_p()
-            _lib.check(lib.vp_create(C.byref(cfg), C.byref(h)), None)
+            # torch's device context is lazy (no cudaSetDevice before the device has a context), so the ordinal is passed
+            # explicitly: the model lives on torch's current device at the time of its first use
+            device = -1
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = int(torch.cuda.current_device())
+            except ImportError:
+                pass
+            _lib.check(lib.vp_create_on_device(C.byref(cfg), device, C.byref(h)), None)
             self._handle = h
         return self._handle
+
+    @property
+    def device_index(self) -> int:
+        """CUDA device ordinal the model (weights, workspace, kernels) lives on."""
+        return int(_lib.lib().vp_handle_device(self._ensure_handle()))
+
+    def _check_device(self, tensor) -> None:
+        if tensor.device.index != self.device_index:
+            raise ValueError(f"input is on cuda:{tensor.device.index} but the model lives on cuda:{self.device_index} "
+                             "(create / load it under `with torch.cuda.device(...)` of the device it should run on)")
 
     def __del__(self):
         try:
@@ -246,6 +265,7 @@ class FactorizedEncoder(_Module):
             import torch
             if not inputs.is_cuda:
                 raise ValueError("torch inputs must live on a CUDA device (pass numpy arrays for host buffers)")
+            self._check_device(inputs)
             is_u8 = inputs.dtype == torch.uint8     # raw decoded frames: / 255 happens on the device (video_utils.py:88-93)
             x = inputs.contiguous() if is_u8 else inputs.to(torch.float32).contiguous()
             fwd = lib.vp_encoder_forward_u8 if is_u8 else lib.vp_encoder_forward
@@ -297,6 +317,7 @@ class FactorizedVideoCLIP(_Module):
             names = [k for k in ("spatial_features", "spatiotemporal_features", "frame_embeddings") if _contains(return_intermediate, k)]
             shapes = {"spatial_features": (b, t * n, d), "spatiotemporal_features": (b, t * n, d), "frame_embeddings": (b, t, d)}
             if _is_torch(inputs):
+                self._check_device(inputs)
                 x = inputs.to(torch.float32).contiguous()
                 video_emb = torch.empty((b, d), dtype=torch.float32, device=x.device)
                 bufs = {k: torch.empty(shapes[k], dtype=torch.float32, device=x.device) for k in names}
@@ -311,8 +332,8 @@ class FactorizedVideoCLIP(_Module):
                 if names or frame_paddings is not None:
                     # host path with intermediates: stage through torch device buffers
                     import torch
-                    xv = torch.from_numpy(np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)).cuda()
-                    fpv = None if frame_paddings is None else torch.from_numpy(np.asarray(frame_paddings, dtype=np.float32)).cuda()
+                    xv = torch.from_numpy(np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)).cuda(self.device_index)
+                    fpv = None if frame_paddings is None else torch.from_numpy(np.asarray(frame_paddings, dtype=np.float32)).cuda(self.device_index)
                     v, _, o = self(xv, None, None, normalize=normalize, return_intermediate=return_intermediate, frame_paddings=fpv)
                     video_emb = v.cpu().numpy()
                     outs.update({k: a.cpu().numpy() for k, a in o.items()})
@@ -327,6 +348,7 @@ class FactorizedVideoCLIP(_Module):
                 raise ValueError("text_token_ids and text_paddings must both be [Q, L]")
             q, length = (int(s) for s in text_token_ids.shape)
             if _is_torch(text_token_ids):
+                self._check_device(text_token_ids)
                 ids = text_token_ids.to(torch.int32).contiguous()
                 pad = torch.as_tensor(text_paddings, device=ids.device).to(torch.float32).contiguous()
                 text_emb = torch.empty((q, d), dtype=torch.float32, device=ids.device)
@@ -370,9 +392,10 @@ class FactorizedVideoClassifier(_Module):
             raise AssertionError("frame_paddings.shape == (b, t)")  # encoders.py:442
         import torch
         host = not _is_torch(inputs)
-        x = torch.from_numpy(np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)).cuda() if host else inputs
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)).cuda(self.device_index) if host else inputs
         if not x.is_cuda:
             raise ValueError("torch inputs must live on a CUDA device (pass numpy arrays for host buffers)")
+        self._check_device(x)
         x = x.to(torch.float32).contiguous()
         names = [k for k in ("spatial_features", "spatiotemporal_features", "global_embeddings") if _contains(return_intermediate, k)]
         shapes = {"spatial_features": (b, t * n, d), "spatiotemporal_features": (b, t * n, d), "global_embeddings": (b, d)}
