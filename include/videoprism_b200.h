@@ -8,8 +8,12 @@
  * vp_last_error); no exception crosses the ABI; the caller owns all I/O buffers and the stream; the
  * handle owns the repacked weights and its workspace; all device work is enqueued on the given
  * stream with no internal host synchronisation (the *_host variants synchronise the stream once,
- * after the device->host copy).  A handle is bound to the CUDA device that was current at vp_create
- * and is not thread-safe.  There is no CPU fallback: without a CUDA device every compute call fails.
+ * after the device->host copy).  A handle is bound to one CUDA device (the current one at vp_create,
+ * or the one named in vp_create_on_device); every entry point selects that device for the duration of
+ * the call and restores the caller's current device before returning.  A handle is not thread-safe,
+ * and because all forwards of a handle share its workspace, consecutive calls on one handle must be
+ * ordered on the device (same stream, or streams the caller orders with events).  There is no CPU
+ * fallback: without a CUDA device every compute call fails.
  */
 #ifndef VIDEOPRISM_B200_H_
 #define VIDEOPRISM_B200_H_

@@ -76,6 +76,27 @@ def test_gpu_ingest_is_bit_exact_with_the_oracle():
 
 
 @pytest.mark.gpu
+def test_gpu_ingest_alignment_and_window_edge_cases():
+    """Frames whose base address and row pitch are not aligned (odd widths, a tensor that starts 1..15 bytes into its
+    allocation and ends at its very last byte: the 32-bit output stores and the gathers must not assume alignment or read
+    past the end), a single frame, strong down-scaling and up-scaling, the identity size: all bit-exact with the oracle."""
+    import torch
+    import videoprism_b200 as vp
+    rng = np.random.default_rng(6)
+    for (t, h, w, target, mode) in [(1, 289, 431, 288, "center_crop"), (2, 361, 643, 288, "resize"), (1, 1080, 1920, 288, "center_crop"),
+                                    (2, 97, 131, 288, "resize"), (3, 300, 299, 144, "center_crop"), (1, 288, 288, 288, "resize")]:
+        frames = rng.integers(0, 256, (t, h, w, 3)).astype(np.uint8)
+        want = np.stack([VO.preprocess_frame_u8(f, target, mode) for f in frames])
+        for offset in (0, 1, 7, 13):
+            flat = torch.zeros(frames.size + offset, dtype=torch.uint8, device="cuda")   # the frames end at the allocation's last byte
+            flat[offset:] = torch.from_numpy(frames.reshape(-1)).cuda()
+            view = flat[offset:].view(t, h, w, 3)
+            assert view.data_ptr() % 16 == (flat.data_ptr() + offset) % 16
+            got = vp.video_utils.preprocess_frames(view, target, mode).cpu().numpy()
+            assert np.array_equal(got, want), (t, h, w, target, mode, offset)
+
+
+@pytest.mark.gpu
 def test_gpu_ingest_feeds_the_encoder():
     """decoded frames -> device resize -> uint8 encoder entry == the float path on the oracle-preprocessed clip, bitwise."""
     import torch
