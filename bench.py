@@ -148,7 +148,10 @@ def run_reference(args):
         "impl": "reference", "metric": "clips/sec (16x288^2 encoder forward)", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": n_steps, "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL_NAME[args.model]} encoder forward, 16x288x288x3 clips", "global_batch": 1},
+        # the same workload as the b200 arm (same string, same global batch); each step is a bounded sample of it: one clip
+        "config": {"workload": f"{MODEL_NAME[args.model]} encoder forward, 16x288x288x3 clips, random-init weights",
+                   "global_batch": args.global_batch, "sample_clips_per_step": 1,
+                   "parallelism": f"{threads} host threads (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "PyTorch-CPU fp32 restatement of the reference Flax path (jax/flax not installable offline)"},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
