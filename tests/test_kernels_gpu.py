@@ -65,7 +65,8 @@ def _close(got, want, rtol=1.5e-2, atol=2e-2):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 768), (4096, 2304, 768), (4096, 768, 3072), (1000, 3072, 768),
-                                   (130, 192, 64), (65, 64, 128), (4096, 768, 1024), (257, 1024, 4096), (8320, 768, 768)])
+                                   (130, 192, 64), (65, 64, 128), (4096, 768, 1024), (257, 1024, 4096), (8320, 768, 768),
+                                   (5000, 32, 768), (129, 32, 64), (300, 24, 176)])   # narrow N: the pooling head's score GEMM
 def test_gemm_plain(L, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = (torch.randn((M, K), device="cuda", generator=g) * 0.5).bfloat16()

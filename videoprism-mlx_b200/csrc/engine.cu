@@ -24,7 +24,7 @@
 
 namespace vp {
 int num_sms();
-cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D, int H, int dh, const float* wkq /*[H,D]*/,
+cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D, int H, int dh, const bf16* wkq /*[32,D] hi|lo*/,
                         const bf16* wv /*[D, H*dh]*/, const float* bv, const bf16* wpost /*[D, H*dh]*/, const float* bpost,
                         const float* ln_g1, const float* ln_b, int normalize, float* scratch, float* out, int64_t* launches);
 size_t pool_scratch_floats(int num_seq, int S, int D, int H, int dh);
@@ -114,7 +114,8 @@ struct vp_handle {
   float *sp_ln_g = nullptr, *sp_ln_b = nullptr, *tp_ln_g = nullptr, *tp_ln_b = nullptr;
   // pooler (collapsed single-query form, see finalize_pooler)
   std::vector<float> h_pool_query, h_pool_wq, h_pool_bq, h_pool_wk, h_pool_pds;
-  float* pool_wkq = nullptr; bf16* pool_wv = nullptr; float* pool_bv = nullptr; bf16* pool_wpost = nullptr;
+  bf16* pool_wkq = nullptr;   // [32, D]: rows h = bf16(wkq[h]), rows H + h = bf16(wkq[h] - that): split-precision score weights
+  bf16* pool_wv = nullptr; float* pool_bv = nullptr; bf16* pool_wpost = nullptr;
   float *pool_bpost = nullptr, *pool_ln_g = nullptr, *pool_ln_b = nullptr;
   int pool_ph = 0;                     // pooler dim_per_head: 4*D/H for the video-text pooler, D/H for the classifier's
   // classifier head (FactorizedVideoClassifier, encoders.py:643-650)
@@ -335,7 +336,7 @@ cudaError_t add_pooler(vp_handle* h, const std::string& pp, int ph) {
   h->pool_ph = ph;
   cudaError_t e;
   vp_handle* hh = h;
-  if ((e = dev_alloc(h, &h->pool_wkq, (size_t)H * D)) != cudaSuccess) return e;
+  if ((e = dev_alloc(h, &h->pool_wkq, (size_t)32 * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &h->pool_wv, (size_t)H * ph * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &h->pool_bv, (size_t)H * ph)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &h->pool_wpost, (size_t)D * H * ph)) != cudaSuccess) return e;
@@ -499,7 +500,18 @@ int finalize_pooler(vp_handle* h) {
       for (int j = 0; j < ph; ++j) acc += (double)h->h_pool_wk[((size_t)d * H + hh) * ph + j] * qh[(size_t)hh * ph + j];
       wkq[(size_t)hh * D + d] = (float)acc;
     }
-  CK(cudaMemcpy(h->pool_wkq, wkq.data(), wkq.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // The scores run on the tensor core (pooling.cu): wkq = hi + lo with both parts in bf16 keeps ~16 mantissa bits of the
+  // folded weight, so the scores stay as accurate as an fp32 dot product of the bf16 tokens would be.
+  if (2 * H > 32) return h->fail(VP_ERR_UNSUPPORTED, "pooling head supports at most 16 heads");
+  std::vector<bf16> hl((size_t)32 * D, __float2bfloat16(0.f));
+  for (int hh = 0; hh < H; ++hh)
+    for (int d = 0; d < D; ++d) {
+      const float w = wkq[(size_t)hh * D + d];
+      const bf16 hi = __float2bfloat16(w);
+      hl[(size_t)hh * D + d] = hi;
+      hl[(size_t)(H + hh) * D + d] = __float2bfloat16(w - __bfloat162float(hi));
+    }
+  CK(cudaMemcpy(h->pool_wkq, hl.data(), hl.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   h->h_pool_wq.clear(); h->h_pool_wq.shrink_to_fit();
   h->h_pool_wk.clear(); h->h_pool_wk.shrink_to_fit();
   return VP_OK;
@@ -1046,9 +1058,11 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   CK(h->ws_pool.ensure((need > need_f ? need : need_f) * sizeof(float)));
   CK(vp::launch_pool(st, x, B, T * N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
                      h->pool_ln_g, h->pool_ln_b, normalize, static_cast<float*>(h->ws_pool.p), video_emb, &h->launches));
+  h->mark(st, "pooler", false);
   if (frame_embeddings) {  // same pooler on the per-frame token sets (:874-885)
     CK(vp::launch_pool(st, x, B * T, N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
                        h->pool_ln_g, h->pool_ln_b, normalize, static_cast<float*>(h->ws_pool.p), frame_embeddings, &h->launches));
+    h->mark(st, "pooler.frames", false);
   }
   return VP_OK;
 }
@@ -1076,6 +1090,7 @@ int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H,
   float* emb = global_embeddings ? global_embeddings : scratch + vp::pool_scratch_floats(B, T * N, D, c.num_heads, ph);
   CK(vp::launch_pool(st, x, B, T * N, D, c.num_heads, ph, h->pool_wkq, h->pool_wv, h->pool_bv, h->pool_wpost, h->pool_bpost,
                      h->pool_ln_g, h->pool_ln_b, 0, scratch, emb, &h->launches));
+  h->mark(st, "pooler", false);
   CK(vp::launch_dense_f32(st, emb, h->cls_w, h->cls_b, logits, B, D, c.num_classes)); h->mark(st, "classifier_projection");
   return VP_OK;
 }
@@ -1100,19 +1115,20 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
   float* keep = static_cast<float*>(h->ws_misc.p);
   float* pad_ext = keep + Mp;
   bf16* x = static_cast<bf16*>(h->ws_x.p);
-  CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->launches++;
+  h->mark(st, nullptr, false);   // trace: start of this forward
+  CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->mark(st, "text.embed");
   SeqLayout tl{Q, S, 1, 1, pad_ext, keep};
   float* stats_a = h->fuse_ln ? static_cast<float*>(h->ws_stats.p) : nullptr;
   float* stats_b = h->fuse_ln ? stats_a + h->stats_stride : nullptr;
-  if (stats_a) { CK(vp::launch_row_stats(st, x, D, stats_a, (int)M, D)); h->launches++; }
+  if (stats_a) { CK(vp::launch_row_stats(st, x, D, stats_a, (int)M, D)); h->mark(st, "text.row_stats"); }
   if ((rc = run_stack(h, h->text, x, (int)M, tl, vp::ACT_RELU, st, stats_a, 1, stats_b, kTagText)) != VP_OK) return rc;
   // unimodal_ln on the class token only (features[:, -1], encoders.py:756-758,:906), then l2 normalise
   float* tmp = static_cast<float*>(h->ws_misc.p) + 2 * Mp;
   vp::LnArgs ln;
   ln.x = x + (size_t)L * D; ln.ldx = S * D; ln.gamma1 = h->uni_ln_g; ln.beta = h->uni_ln_b;
   ln.y_f32 = normalize ? tmp : text_emb; ln.M = Q; ln.D = D;
-  CK(vp::launch_layernorm(st, ln)); h->launches++;
-  if (normalize) { CK(vp::launch_l2norm(st, tmp, text_emb, Q, D)); h->launches++; }
+  CK(vp::launch_layernorm(st, ln)); h->mark(st, "text.unimodal_ln");
+  if (normalize) { CK(vp::launch_l2norm(st, tmp, text_emb, Q, D)); h->mark(st, "text.l2norm"); }
   return VP_OK;
 }
 

@@ -31,134 +31,183 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// scores[row, h] = x[row, :] . wkq[h, :]      (one warp per row, wkq staged in smem)
-__global__ void __launch_bounds__(256) pool_scores_kernel(const bf16* __restrict__ x, const float* __restrict__ wkq,
-                                                          float* __restrict__ scores, int rows, int D, int H) {
-  extern __shared__ float s_w[];  // [H][D]
-  for (int i = threadIdx.x; i < H * D; i += blockDim.x) s_w[i] = wkq[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int row = blockIdx.x * wpb + warp; row < rows; row += gridDim.x * wpb) {
-    float acc[kMaxHeads];
-#pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) acc[h] = 0.f;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * D);
-    for (int vi = lane; vi < D / 8; vi += 32) {
-      const uint4 u = xr[vi];
-      float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-#pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) {
-        if (h < H) {
-          const float4 w0 = *reinterpret_cast<const float4*>(s_w + h * D + vi * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(s_w + h * D + vi * 8 + 4);
-          acc[h] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y + xv[6] * w1.z + xv[7] * w1.w;
-        }
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) {
-      if (h < H) {
-        const float v = warp_sum(acc[h]);
-        if (lane == 0) scores[static_cast<size_t>(row) * H + h] = v;
-      }
-    }
-  }
-}
+// scores[row, 0..31] = x[row, :] . wkq_hl[0..31, :] comes from the tcgen05 GEMM (fp32 accumulators written as they are):
+// columns h and H + h hold the products with the high and the low bf16 part of the folded weight; their sum is the score.
+constexpr int kScoreLd = 32;
 
-// stats[seq, h] = (max_s scores, sum_s exp(scores - max))    (one block per sequence, one warp per head in turn)
+// stats[seq, h] = (max_s scores, sum_s exp(scores - max))    grid (H, num_seq): one block per (head, sequence)
 __global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict__ scores, float* __restrict__ stats, int S, int H) {
-  const int seq = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* sc = scores + static_cast<size_t>(seq) * S * H;
-  for (int h = warp; h < H; h += nw) {
-    float m = -CUDART_INF_F;
-    for (int s = lane; s < S; s += 32) m = fmaxf(m, sc[static_cast<size_t>(s) * H + h]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int s = lane; s < S; s += 32) sum += __expf(sc[static_cast<size_t>(s) * H + h] - m);
-    sum = warp_sum(sum);
-    if (lane == 0) {
-      stats[(static_cast<size_t>(seq) * H + h) * 2 + 0] = m;
-      stats[(static_cast<size_t>(seq) * H + h) * 2 + 1] = sum;
-    }
+  __shared__ float s_red[8];
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* sc = scores + static_cast<size_t>(seq) * S * kScoreLd + h;
+  float m = -CUDART_INF_F;
+  for (int s = threadIdx.x; s < S; s += 256) m = fmaxf(m, sc[static_cast<size_t>(s) * kScoreLd] + sc[static_cast<size_t>(s) * kScoreLd + H]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int s = threadIdx.x; s < S; s += 256) sum += __expf(sc[static_cast<size_t>(s) * kScoreLd] + sc[static_cast<size_t>(s) * kScoreLd + H] - m);
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w];   // fixed order: deterministic
+    stats[(static_cast<size_t>(seq) * H + h) * 2 + 0] = m;
+    stats[(static_cast<size_t>(seq) * H + h) * 2 + 1] = t;
   }
 }
 
-// partial[seq, chunk, h, d] = sum_{s in chunk} p[s,h] x[s,d]
+// partial[seq, chunk, h, d] = sum_{s in chunk} p[s,h] x[s,d]     grid (nchunk, num_seq); each thread owns 4 consecutive
+// feature columns (one 8-byte load per token) and all heads: the probabilities of the chunk sit in shared memory.
 __global__ void __launch_bounds__(256) pool_accum_kernel(const bf16* __restrict__ x, const float* __restrict__ scores,
                                                          const float* __restrict__ stats, float* __restrict__ partial, int S, int D,
                                                          int H, int nchunk) {
-  __shared__ float s_p[kChunk][kMaxHeads];
+  __shared__ __align__(16) float s_p[kChunk][kMaxHeads];
   const int chunk = blockIdx.x, seq = blockIdx.y;
   const int s0 = chunk * kChunk;
   const int ns = min(kChunk, S - s0);
-  for (int i = threadIdx.x; i < ns * H; i += blockDim.x) {
-    const int s = i / H, h = i % H;
-    const float m = stats[(static_cast<size_t>(seq) * H + h) * 2 + 0];
-    const float sum = stats[(static_cast<size_t>(seq) * H + h) * 2 + 1];
-    s_p[s][h] = __expf(scores[(static_cast<size_t>(seq) * S + s0 + s) * H + h] - m) / sum;
+  for (int i = threadIdx.x; i < ns * kMaxHeads; i += blockDim.x) {
+    const int s = i / kMaxHeads, h = i % kMaxHeads;
+    float p = 0.f;
+    if (h < H) {
+      const float m = stats[(static_cast<size_t>(seq) * H + h) * 2 + 0];
+      const float sum = stats[(static_cast<size_t>(seq) * H + h) * 2 + 1];
+      const float* sr = scores + (static_cast<size_t>(seq) * S + s0 + s) * kScoreLd;
+      p = __expf(sr[h] + sr[H + h] - m) / sum;
+    }
+    s_p[s][h] = p;
   }
   __syncthreads();
-  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
-    const int d = d0 + threadIdx.x;
-    if (d >= D) break;
-    float acc[kMaxHeads];
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {   // D % 8 == 0
+    float acc[kMaxHeads][4];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) acc[h] = 0.f;
+    for (int h = 0; h < kMaxHeads; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
     const bf16* xp = x + (static_cast<size_t>(seq) * S + s0) * D + d;
+#pragma unroll 2
     for (int s = 0; s < ns; ++s) {
-      const float xv = __bfloat162float(xp[static_cast<size_t>(s) * D]);
+      const uint2 u = *reinterpret_cast<const uint2*>(xp + static_cast<size_t>(s) * D);
+      const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) acc[h] += s_p[s][h] * xv;   // rows of s_p beyond H hold stale data but are never stored
+      for (int h4 = 0; h4 < kMaxHeads / 4; ++h4) {
+        const float4 p = *reinterpret_cast<const float4*>(&s_p[s][h4 * 4]);
+        const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float* a = acc[h4 * 4 + k];
+          a[0] = fmaf(pv[k], x0, a[0]); a[1] = fmaf(pv[k], x1, a[1]); a[2] = fmaf(pv[k], x2, a[2]); a[3] = fmaf(pv[k], x3, a[3]);
+        }
+      }
     }
-    float* pp = partial + (static_cast<size_t>(seq) * nchunk + chunk) * H * D;
+    float* pp = partial + (static_cast<size_t>(seq) * nchunk + chunk) * H * D + d;
 #pragma unroll
     for (int h = 0; h < kMaxHeads; ++h)
-      if (h < H) pp[static_cast<size_t>(h) * D + d] = acc[h];
+      if (h < H) *reinterpret_cast<float4*>(pp + static_cast<size_t>(h) * D) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
   }
 }
 
-// ctx[seq, h*dh + j] = (sum_chunks partial[seq, :, h, :]) . Wv[:, h, j] + bv[h, j]     grid (H, num_seq), block dh
-__global__ void pool_ctx_kernel(const float* __restrict__ partial, const bf16* __restrict__ wv /*[D, H*dh]*/,
-                                const float* __restrict__ bv, float* __restrict__ ctx, int D, int H, int dh, int nchunk) {
-  extern __shared__ float s_xbar[];  // [D]
-  const int h = blockIdx.x, seq = blockIdx.y;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < nchunk; ++c) a += partial[((static_cast<size_t>(seq) * nchunk + c) * H + h) * D + d];
-    s_xbar[d] = a;
+// xbar[seq, h, d] = sum_chunks partial[seq, chunk, h, d]   (chunk order: deterministic)
+__global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restrict__ partial, float* __restrict__ xbar, int HD_in,
+                                                          int nchunk, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over num_seq * H * D
+  if (i >= total) return;
+  const size_t seq = i / HD_in, r = i % HD_in;
+  const float* pp = partial + seq * nchunk * HD_in + r;
+  float a = 0.f;
+  for (int c = 0; c < nchunk; ++c) a += pp[static_cast<size_t>(c) * HD_in];
+  xbar[i] = a;
+}
+
+// ctx[seq, h*dh + j] = xbar[seq, h, :] . Wv[:, h, j] + bv[h, j]
+// grid (H * dh / blockDim, ceil(num_seq / kSeqTile)); a block owns blockDim columns of ONE head (blockDim = min(dh, 128))
+// and kSeqTile sequences, so every weight element is read once per tile of sequences instead of once per sequence.
+constexpr int kSeqTile = 8;
+constexpr int kDTile = 64;
+__global__ void __launch_bounds__(128) pool_ctx_kernel(const float* __restrict__ xbar, const bf16* __restrict__ wv /*[D, H*dh]*/,
+                                                       const float* __restrict__ bv, float* __restrict__ ctx, int D, int H, int dh,
+                                                       int num_seq) {
+  __shared__ __align__(16) float s_x[kDTile][kSeqTile];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // = h * dh + j
+  const int h = (blockIdx.x * blockDim.x) / dh;
+  const int seq0 = blockIdx.y * kSeqTile;
+  const int HD = H * dh;
+  float acc[kSeqTile];
+#pragma unroll
+  for (int q = 0; q < kSeqTile; ++q) acc[q] = 0.f;
+  for (int d0 = 0; d0 < D; d0 += kDTile) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDTile * kSeqTile; i += blockDim.x) {
+      const int q = i / kDTile, dd = i % kDTile;   // consecutive threads read consecutive d: coalesced
+      const int seq = seq0 + q, d = d0 + dd;
+      s_x[dd][q] = (seq < num_seq && d < D) ? xbar[(static_cast<size_t>(seq) * H + h) * D + d] : 0.f;
+    }
+    __syncthreads();
+    const int dmax = min(kDTile, D - d0);
+    const bf16* wp = wv + static_cast<size_t>(d0) * HD + col;
+#pragma unroll 4
+    for (int dd = 0; dd < dmax; ++dd) {
+      const float w = __bfloat162float(wp[static_cast<size_t>(dd) * HD]);
+      const float4 a = *reinterpret_cast<const float4*>(&s_x[dd][0]);
+      const float4 b = *reinterpret_cast<const float4*>(&s_x[dd][4]);
+      acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+      acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]); acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
+    }
   }
-  __syncthreads();
-  const int j = threadIdx.x;
-  if (j < dh) {
-    float a = 0.f;
-    const bf16* wp = wv + static_cast<size_t>(h) * dh + j;
-    for (int d = 0; d < D; ++d) a += s_xbar[d] * __bfloat162float(wp[static_cast<size_t>(d) * H * dh]);
-    ctx[static_cast<size_t>(seq) * H * dh + h * dh + j] = a + bv[h * dh + j];
+  const float bias = bv[col];
+#pragma unroll
+  for (int q = 0; q < kSeqTile; ++q)
+    if (seq0 + q < num_seq) ctx[static_cast<size_t>(seq0 + q) * HD + col] = acc[q] + bias;
+}
+
+// y[seq, d] = ctx[seq, :] . wpost[d, :] + bpost[d]     grid (ceil(D / 8), ceil(num_seq / kSeqTile)), one warp per output
+// feature d and kSeqTile sequences: the weight row is read once per tile, the ctx rows come from L1 / L2.
+__global__ void __launch_bounds__(256) pool_post_kernel(const float* __restrict__ ctx, const bf16* __restrict__ wpost /*[D, HD]*/,
+                                                        const float* __restrict__ bpost, float* __restrict__ y, int D, int HD,
+                                                        int num_seq) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = blockIdx.x * 8 + warp;
+  const int seq0 = blockIdx.y * kSeqTile;
+  if (d >= D) return;
+  float acc[kSeqTile];
+#pragma unroll
+  for (int q = 0; q < kSeqTile; ++q) acc[q] = 0.f;
+  const bf16* wr = wpost + static_cast<size_t>(d) * HD;
+  for (int i = lane * 8; i < HD; i += 256) {   // HD % 8 == 0
+    const uint4 u = *reinterpret_cast<const uint4*>(wr + i);
+    const float w[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+    for (int q = 0; q < kSeqTile; ++q) {
+      if (seq0 + q < num_seq) {
+        const float* cp = ctx + static_cast<size_t>(seq0 + q) * HD + i;
+        const float4 c0 = *reinterpret_cast<const float4*>(cp);
+        const float4 c1 = *reinterpret_cast<const float4*>(cp + 4);
+        acc[q] += c0.x * w[0] + c0.y * w[1] + c0.z * w[2] + c0.w * w[3] + c1.x * w[4] + c1.y * w[5] + c1.z * w[6] + c1.w * w[7];
+      }
+    }
+  }
+  const float bias = bpost[d];
+#pragma unroll
+  for (int q = 0; q < kSeqTile; ++q) {
+    const float v = warp_sum(acc[q]);
+    if (lane == 0 && seq0 + q < num_seq) y[static_cast<size_t>(seq0 + q) * D + d] = v + bias;
   }
 }
 
-// out[seq, :] = [l2norm] LN( ctx[seq, :] . wpost[d, :] + bpost[d] )       one block per sequence
-__global__ void __launch_bounds__(256) pool_out_kernel(const float* __restrict__ ctx, const bf16* __restrict__ wpost /*[D, HD]*/,
-                                                       const float* __restrict__ bpost, const float* __restrict__ g1,
-                                                       const float* __restrict__ beta, float* __restrict__ out, int D, int HD,
-                                                       int normalize) {
-  extern __shared__ float sm[];  // ctx [HD] | y [D] | red [32]
-  float* s_ctx = sm;
-  float* s_y = sm + HD;
+// out[seq, :] = [l2norm] LN( y[seq, :] )       one block per sequence
+__global__ void __launch_bounds__(256) pool_norm_kernel(const float* __restrict__ y, const float* __restrict__ g1,
+                                                        const float* __restrict__ beta, float* __restrict__ out, int D, int normalize) {
+  extern __shared__ float sm[];  // y [D] | red [32]
+  float* s_y = sm;
   float* s_red = s_y + D;
   const int seq = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < HD; i += blockDim.x) s_ctx[i] = ctx[static_cast<size_t>(seq) * HD + i];
-  __syncthreads();
-  for (int d = warp; d < D; d += nw) {
-    const bf16* wr = wpost + static_cast<size_t>(d) * HD;
-    float a = 0.f;
-    for (int i = lane; i < HD; i += 32) a += s_ctx[i] * __bfloat162float(wr[i]);
-    a = warp_sum(a);
-    if (lane == 0) s_y[d] = a + bpost[d];
-  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s_y[d] = y[static_cast<size_t>(seq) * D + d];
   __syncthreads();
   auto block_sum = [&](float v) {
     v = warp_sum(v);
@@ -182,9 +231,9 @@ __global__ void __launch_bounds__(256) pool_out_kernel(const float* __restrict__
   const float rstd = rsqrtf(block_sum(sq) / D + 1e-6f);
   float nn = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float y = (s_y[d] - mean) * rstd * g1[d] + beta[d];
-    s_y[d] = y;
-    nn += y * y;
+    const float v = (s_y[d] - mean) * rstd * g1[d] + beta[d];
+    s_y[d] = v;
+    nn += v * v;
   }
   const float tot = block_sum(nn);
   const float inv = normalize ? 1.0f / sqrtf(tot + 1e-12f) : 1.0f;
@@ -244,43 +293,63 @@ __global__ void __launch_bounds__(256) dense_f32_kernel(const float* __restrict_
 
 }  // namespace
 
-size_t pool_scratch_floats(int num_seq, int S, int D, int H, int dh) {
-  const size_t nchunk = (S + kChunk - 1) / kChunk;
-  return static_cast<size_t>(num_seq) * S * H + static_cast<size_t>(num_seq) * H * 2 + static_cast<size_t>(num_seq) * nchunk * H * D +
-         static_cast<size_t>(num_seq) * H * dh + 64;
-}
+namespace {
+inline size_t align4(size_t n) { return (n + 3) & ~static_cast<size_t>(3); }   // sub-buffers start on 16-byte boundaries
+struct PoolScratch {
+  size_t scores, stats, partial, xbar, ctx, y, end;
+  PoolScratch(int num_seq, int S, int D, int H, int dh) {
+    const size_t n = static_cast<size_t>(num_seq), nchunk = (S + kChunk - 1) / kChunk;
+    scores = 0;
+    stats = align4(scores + n * S * kScoreLd);
+    partial = align4(stats + n * H * 2);
+    xbar = align4(partial + n * nchunk * H * D);
+    ctx = align4(xbar + n * H * D);
+    y = align4(ctx + n * H * dh);
+    end = align4(y + n * D);
+  }
+};
+}  // namespace
 
-cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D, int H, int dh, const float* wkq, const bf16* wv,
+size_t pool_scratch_floats(int num_seq, int S, int D, int H, int dh) { return PoolScratch(num_seq, S, D, H, dh).end + 64; }
+
+cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D, int H, int dh, const bf16* wkq, const bf16* wv,
                         const float* bv, const bf16* wpost, const float* bpost, const float* ln_g1, const float* ln_b, int normalize,
                         float* scratch, float* out, int64_t* launches) {
-  if (H > kMaxHeads || (D % 8) || dh > 1024) return cudaErrorInvalidValue;
+  const int HD = H * dh;
+  const int ctx_threads = dh < 128 ? dh : 128;
+  if (H > kMaxHeads || 2 * H > kScoreLd || (D % 8) || (dh % 8) || dh > 1024 || (dh % ctx_threads) || num_seq <= 0 || S <= 0) return cudaErrorInvalidValue;
+  if (reinterpret_cast<uintptr_t>(scratch) & 15) return cudaErrorInvalidValue;
   const int nchunk = (S + kChunk - 1) / kChunk;
-  float* scores = scratch;
-  float* stats = scores + static_cast<size_t>(num_seq) * S * H;
-  float* partial = stats + static_cast<size_t>(num_seq) * H * 2;
-  float* ctx = partial + static_cast<size_t>(num_seq) * nchunk * H * D;
-  const int rows = num_seq * S;
+  const size_t n = static_cast<size_t>(num_seq);
+  const PoolScratch off(num_seq, S, D, H, dh);
+  float* scores = scratch + off.scores;
+  float* stats = scratch + off.stats;
+  float* partial = scratch + off.partial;
+  float* xbar = scratch + off.xbar;
+  float* ctx = scratch + off.ctx;
+  float* y = scratch + off.y;
   cudaError_t e;
   {
-    const size_t smem = static_cast<size_t>(H) * D * sizeof(float);
-    static int granted[kMaxDevices] = {};
-    if (smem > 48 * 1024 && (e = ensure_dynamic_smem(pool_scores_kernel, static_cast<int>(smem), granted)) != cudaSuccess) return e;
-    int grid = (rows + 7) / 8;
-    if (grid > 148 * 8) grid = 148 * 8;
-    pool_scores_kernel<<<grid, 256, smem, s>>>(x, wkq, scores, rows, D, H);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    GemmEpilogue ep;
+    ep.out_f32 = 1;
+    if ((e = launch_gemm(s, x, D, wkq, D, scores, kScoreLd, num_seq * S, kScoreLd, D, ep)) != cudaSuccess) return e;
   }
-  pool_stats_kernel<<<num_seq, 256, 0, s>>>(scores, stats, S, H);
+  pool_stats_kernel<<<dim3(H, num_seq), 256, 0, s>>>(scores, stats, S, H);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  pool_accum_kernel<<<dim3(nchunk, num_seq), 256, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk);
+  const int accum_threads = D / 4 >= 256 ? 256 : ((D / 4 + 31) / 32) * 32;
+  pool_accum_kernel<<<dim3(nchunk, num_seq), accum_threads, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const int ctx_threads = ((dh + 31) / 32) * 32;
-  pool_ctx_kernel<<<dim3(H, num_seq), ctx_threads, D * sizeof(float), s>>>(partial, wv, bv, ctx, D, H, dh, nchunk);
+  const size_t total = n * H * D;
+  pool_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(partial, xbar, H * D, nchunk, total);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  pool_out_kernel<<<num_seq, 256, (static_cast<size_t>(H) * dh + D + 32) * sizeof(float), s>>>(ctx, wpost, bpost, ln_g1, ln_b, out, D,
-                                                                                                H * dh, normalize);
+  const int seq_tiles = (num_seq + kSeqTile - 1) / kSeqTile;
+  pool_ctx_kernel<<<dim3(HD / ctx_threads, seq_tiles), ctx_threads, 0, s>>>(xbar, wv, bv, ctx, D, H, dh, num_seq);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (launches) *launches += 5;
+  pool_post_kernel<<<dim3((D + 7) / 8, seq_tiles), 256, 0, s>>>(ctx, wpost, bpost, y, D, HD, num_seq);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  pool_norm_kernel<<<num_seq, 256, (static_cast<size_t>(D) + 32) * sizeof(float), s>>>(y, ln_g1, ln_b, out, D, normalize);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (launches) *launches += 7;
   return cudaSuccess;
 }
 
