@@ -7,7 +7,8 @@
 //   ctx[h,:]    = sum_s p[s,h] v[s,h,:] = (sum_s p[s,h] x[s]) . Wv[:,h,:] + bv[h,:]
 //   out         = LN( ctx . post.w + post.b ) ; optional l2 normalise (encoders.py:50-67)
 // which replaces the reference's [S,D]x[D,4D] key/value projections (38.7 GF per base clip) by two
-// passes over x (0.15 GF); everything here is bandwidth-bound fp32 CUDA-core work.
+// passes over x (0.15 GF): the score pass runs on the tensor core (launch_gemm), the rest is bandwidth- / latency-bound
+// fp32 CUDA-core work laid out for parallelism across sequences (a retrieval batch pools 32+ sequences at once).
 #include <math_constants.h>
 
 #include "kernels.h"
@@ -35,37 +36,38 @@ __device__ __forceinline__ float warp_max(float v) {
 // columns h and H + h hold the products with the high and the low bf16 part of the folded weight; their sum is the score.
 constexpr int kScoreLd = 32;
 
-// stats[seq, h] = (max_s scores, sum_s exp(scores - max))    grid (H, num_seq): one block per (head, sequence)
-__global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict__ scores, float* __restrict__ stats, int S, int H) {
-  __shared__ float s_red[8];
-  const int h = blockIdx.x, seq = blockIdx.y;
+// stats[seq, h] = (max_s scores, sum_s exp(scores - max))    one block of 32 warps per sequence.  A warp reads whole score
+// rows (32 floats = one 128-byte line: lane h and lane H + h hold the two parts of head h's score) and keeps a running
+// (max, sum) per lane; the 32 warps are merged in a fixed order.
+__global__ void __launch_bounds__(1024) pool_stats_kernel(const float* __restrict__ scores, float* __restrict__ stats, int S, int H) {
+  __shared__ float s_m[32][kMaxHeads], s_l[32][kMaxHeads];
+  const int seq = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* sc = scores + static_cast<size_t>(seq) * S * kScoreLd + h;
-  float m = -CUDART_INF_F;
-  for (int s = threadIdx.x; s < S; s += 256) m = fmaxf(m, sc[static_cast<size_t>(s) * kScoreLd] + sc[static_cast<size_t>(s) * kScoreLd + H]);
-  m = warp_max(m);
-  if (lane == 0) s_red[warp] = m;
+  const float* sc = scores + static_cast<size_t>(seq) * S * kScoreLd;
+  float m = -CUDART_INF_F, l = 0.f;
+  for (int s = warp; s < S; s += 32) {
+    const float r = sc[static_cast<size_t>(s) * kScoreLd + lane];
+    const float v = r + __shfl_sync(0xffffffffu, r, (lane + H) & 31);   // meaningful for lane < H
+    const float mn = fmaxf(m, v);
+    l = l * __expf(m - mn) + __expf(v - mn);
+    m = mn;
+  }
+  if (lane < kMaxHeads) { s_m[warp][lane] = m; s_l[warp][lane] = l; }
   __syncthreads();
-  m = s_red[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int s = threadIdx.x; s < S; s += 256) sum += __expf(sc[static_cast<size_t>(s) * kScoreLd] + sc[static_cast<size_t>(s) * kScoreLd + H] - m);
-  sum = warp_sum(sum);
-  if (lane == 0) s_red[warp] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < H) {
+    const int h = threadIdx.x;
+    float mm = s_m[0][h];
+    for (int w = 1; w < 32; ++w) mm = fmaxf(mm, s_m[w][h]);
     float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_red[w];   // fixed order: deterministic
-    stats[(static_cast<size_t>(seq) * H + h) * 2 + 0] = m;
+    for (int w = 0; w < 32; ++w) t += s_l[w][h] * __expf(s_m[w][h] - mm);   // warps without rows: l = 0, exp(-inf) = 0
+    stats[(static_cast<size_t>(seq) * H + h) * 2 + 0] = mm;
     stats[(static_cast<size_t>(seq) * H + h) * 2 + 1] = t;
   }
 }
 
 // partial[seq, chunk, h, d] = sum_{s in chunk} p[s,h] x[s,d]     grid (nchunk, num_seq); each thread owns 4 consecutive
 // feature columns (one 8-byte load per token) and all heads: the probabilities of the chunk sit in shared memory.
+template <int HG>   // head groups of 4 actually accumulated: ceil(H / 4)
 __global__ void __launch_bounds__(256) pool_accum_kernel(const bf16* __restrict__ x, const float* __restrict__ scores,
                                                          const float* __restrict__ stats, float* __restrict__ partial, int S, int D,
                                                          int H, int nchunk) {
@@ -86,16 +88,16 @@ __global__ void __launch_bounds__(256) pool_accum_kernel(const bf16* __restrict_
   }
   __syncthreads();
   for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {   // D % 8 == 0
-    float acc[kMaxHeads][4];
+    float acc[HG * 4][4];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+    for (int h = 0; h < HG * 4; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
     const bf16* xp = x + (static_cast<size_t>(seq) * S + s0) * D + d;
-#pragma unroll 2
+#pragma unroll 4
     for (int s = 0; s < ns; ++s) {
       const uint2 u = *reinterpret_cast<const uint2*>(xp + static_cast<size_t>(s) * D);
       const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
 #pragma unroll
-      for (int h4 = 0; h4 < kMaxHeads / 4; ++h4) {
+      for (int h4 = 0; h4 < HG; ++h4) {
         const float4 p = *reinterpret_cast<const float4*>(&s_p[s][h4 * 4]);
         const float pv[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) pool_accum_kernel(const bf16* __restrict_
     }
     float* pp = partial + (static_cast<size_t>(seq) * nchunk + chunk) * H * D + d;
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h)
+    for (int h = 0; h < HG * 4; ++h)
       if (h < H) *reinterpret_cast<float4*>(pp + static_cast<size_t>(h) * D) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
   }
 }
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(128) pool_ctx_kernel(const float* __restrict__
     __syncthreads();
     const int dmax = min(kDTile, D - d0);
     const bf16* wp = wv + static_cast<size_t>(d0) * HD + col;
-#pragma unroll 4
+#pragma unroll 16
     for (int dd = 0; dd < dmax; ++dd) {
       const float w = __bfloat162float(wp[static_cast<size_t>(dd) * HD]);
       const float4 a = *reinterpret_cast<const float4*>(&s_x[dd][0]);
@@ -334,10 +336,15 @@ cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D
     ep.out_f32 = 1;
     if ((e = launch_gemm(s, x, D, wkq, D, scores, kScoreLd, num_seq * S, kScoreLd, D, ep)) != cudaSuccess) return e;
   }
-  pool_stats_kernel<<<dim3(H, num_seq), 256, 0, s>>>(scores, stats, S, H);
+  pool_stats_kernel<<<num_seq, 1024, 0, s>>>(scores, stats, S, H);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int accum_threads = D / 4 >= 256 ? 256 : ((D / 4 + 31) / 32) * 32;
-  pool_accum_kernel<<<dim3(nchunk, num_seq), accum_threads, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk);
+  switch ((H + 3) / 4) {
+    case 1: pool_accum_kernel<1><<<dim3(nchunk, num_seq), accum_threads, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk); break;
+    case 2: pool_accum_kernel<2><<<dim3(nchunk, num_seq), accum_threads, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk); break;
+    case 3: pool_accum_kernel<3><<<dim3(nchunk, num_seq), accum_threads, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk); break;
+    default: pool_accum_kernel<4><<<dim3(nchunk, num_seq), accum_threads, 0, s>>>(x, scores, stats, partial, S, D, H, nchunk); break;
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const size_t total = n * H * D;
   pool_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(partial, xbar, H * D, nchunk, total);
