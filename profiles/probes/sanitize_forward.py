@@ -1,8 +1,12 @@
-"""One pass over every kernel family for compute-sanitizer (memcheck): tiny encoder with frame paddings, tiny video-text
-model with ragged text, tiny classifier, one full-size base clip (tcgen05 GEMM pair path, S=256 tcgen05 attention,
-folded LayerNorm), one full-size video-text clip (S=4096 key-loop attention, pooler), frame ingest.
+"""One pass over every kernel family, written for compute-sanitizer (memcheck): tiny encoder with frame paddings, tiny
+video-text model with ragged text, tiny classifier, one full-size base clip (tcgen05 GEMM pair path, S=256 tcgen05
+attention, folded LayerNorm), one full-size video-text clip (S=4096 key-loop attention, pooler), frame ingest.
 
     compute-sanitizer --tool memcheck --error-exitcode 9 python profiles/probes/sanitize_forward.py
+
+compute-sanitizer is closed on this GPU pool (gpurun refuses it: runs under it have left GPUs needing a reset), so in
+round 1 this ran plainly, as an all-kernels smoke; out-of-bounds protection rests on the alignment / buffer-end / ragged
+shape tests in tests/ (test_gpu_ingest_alignment_and_window_edge_cases, test_base_encoder_ragged_shapes, test_attention).
 """
 import os
 import sys
