@@ -1181,9 +1181,21 @@ size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W) {
   if (!h || B <= 0 || T <= 0 || H <= 0 || W <= 0) return 0;
   const vp_config& c = h->cfg;
   const size_t N = (size_t)(H / c.patch_size) * (W / c.patch_size);
-  const size_t M = (size_t)B * T * N;
+  if (N == 0) return 0;
+  const size_t tokens_per_clip = (size_t)T * N;
+  size_t clips = (size_t)B;
+  if (c.kind == VP_KIND_ENCODER) {   // the encoder entry points run at most 2^18 tokens per pass (encoder_forward_dev)
+    const size_t max_clips = std::max<size_t>(1, ((size_t)1 << 18) / tokens_per_clip);
+    clips = std::min(clips, max_clips);
+  }
+  const size_t M = clips * tokens_per_clip;
   const size_t D = c.model_dim, F = c.mlp_dim;
-  return M * (5 * D + F + h->k_patch_pad) * sizeof(bf16);
+  size_t bytes = M * (5 * D + F + h->k_patch_pad) * sizeof(bf16);                 // x, n, qkv (3D), u, patches
+  const size_t slots = std::max(vp::gemm_stats_slots((int)D), 16);
+  bytes += 2 * (M * 2 * slots + 64) * sizeof(float);                              // LayerNorm row statistics (two buffers)
+  if (c.kind != VP_KIND_ENCODER)                                                  // pooling-head scratch
+    bytes += vp::pool_scratch_floats((int)clips, (int)tokens_per_clip, (int)D, c.num_heads, h->pool_ph) * sizeof(float);
+  return bytes;
 }
 
 int64_t vp_kernel_launches(const vp_handle* h) { return h ? h->launches : 0; }
