@@ -145,6 +145,9 @@ VP_API int vp_similarity(const float* v, const float* t, float* sim, int Nv, int
 
 /* -- introspection ------------------------------------------------------------------------------- */
 VP_API size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W); /* device bytes a forward of this shape needs */
+/* Frees the activation workspace (it grows to the largest batch seen and is otherwise kept until vp_destroy); weights stay.
+ * Waits for the handle's device to be idle.  The next forward allocates what it needs again. */
+VP_API int vp_release_workspace(vp_handle* h);
 VP_API int64_t vp_kernel_launches(const vp_handle* h);  /* kernels launched by this handle so far */
 VP_API int vp_device_sm_count(void);                    /* < 0 when no CUDA device is usable */
 /* In-situ timeline (diagnostic; the reference's counterpart is scripts/benchmark_performance.py's per-stage timers):

@@ -424,3 +424,19 @@ def test_benchmark_performance_script_runs_with_synthetic_fallbacks():
     assert r.returncode == 0, r.stderr[-2000:]
     assert "mean=" in r.stdout and "video embeddings (1, 768), text embeddings (3, 768)" in r.stdout
     assert "synthetic uniform frames" in r.stdout and "synthetic token ids" in r.stdout
+
+
+def test_release_workspace_frees_memory_and_the_next_forward_is_unchanged():
+    import videoprism_b200 as vp
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    m = vp.get_model("videoprism_public_v1_base")
+    m.load_state(O.make_synthetic_weights(cfg))
+    v = torch.from_numpy(O.make_video(4, 16, 288, seed=41)).cuda()
+    a, _ = m(v)
+    torch.cuda.synchronize()
+    free_before, _ = torch.cuda.mem_get_info()
+    m.release_workspace()
+    free_after, _ = torch.cuda.mem_get_info()
+    assert free_after - free_before > 150 * 2**20      # 4 clips: x, n, qkv, u, patches ~ 250 MB
+    b, _ = m(v[:2])
+    assert torch.equal(a[:2], b)

@@ -48,6 +48,7 @@ _PROTOS = {
     "vp_classifier_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "vp_similarity": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "vp_workspace_bytes": (C.c_size_t, [_P, _I, _I, _I, _I]),
+    "vp_release_workspace": (_I, [_P]),
     "vp_kernel_launches": (C.c_int64, [_P]),
     "vp_device_sm_count": (_I, []),
     "vp_trace": (_I, [_P, _I]),

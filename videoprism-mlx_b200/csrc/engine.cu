@@ -1198,6 +1198,16 @@ size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W) {
   return bytes;
 }
 
+int vp_release_workspace(vp_handle* h) {
+  if (h == nullptr) return VP_ERR_INVALID;
+  DeviceScope device_scope(h->device);
+  // cudaFree waits for the device: forwards still in flight finish first.  The buffers grow again on the next call.
+  DevBuf* bufs[] = {&h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats};
+  for (DevBuf* b : bufs) b->release();
+  h->stats_stride = 0;
+  return VP_OK;
+}
+
 int64_t vp_kernel_launches(const vp_handle* h) { return h ? h->launches : 0; }
 
 // In-situ timeline: with tracing on, every launch is followed by a CUDA event on the launch stream; the report

@@ -203,6 +203,12 @@ class _Module:
         self._bind(variables)
         return self(*args, **kwargs)
 
+    def release_workspace(self) -> None:
+        """Frees the activation workspace (sized for the largest batch seen so far); weights stay loaded.  The next call
+        allocates again: for servers that see one large batch and then go back to small ones."""
+        if self._handle is not None:
+            _lib.check(_lib.lib().vp_release_workspace(self._handle), self._handle)
+
     @property
     def kernel_launches(self) -> int:
         return int(_lib.lib().vp_kernel_launches(self._handle)) if self._handle is not None else 0
