@@ -45,6 +45,31 @@ def test_oracle_matches_live_cv2_on_random_sizes():
         assert np.array_equal(VO.preprocess_frame_u8(img, 288, "center_crop"), ref[y0:y0 + 288, x0:x0 + 288])
 
 
+REF_MP4 = "/root/reference/videoprism/assets/water_bottle_drumming.mp4"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MP4), reason="reference mp4 fixture not on this box")
+@pytest.mark.parametrize("mode", ["center_crop", "resize"])
+def test_whole_host_chain_equals_the_reference_load_video_on_its_own_fixture(mode):
+    """The reference's video_utils.load_video, imported from where it lies and run UNMODIFIED on its own mp4 fixture,
+    against this repo's frame sampling (video_utils.read_frames) followed by the ingest oracle: float32 clip, bit for bit.
+    (The device resize is held to the same oracle in the GPU tests, so the three agree.)"""
+    pytest.importorskip("cv2")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_video_utils", "/root/reference/videoprism/video_utils.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    want = ref.load_video(REF_MP4, num_frames=16, target_size=288, resize_mode=mode)
+    from videoprism_b200 import video_utils
+    frames = video_utils.read_frames(REF_MP4, 16)
+    assert frames.dtype == np.uint8 and frames.shape[0] == 16 and frames.shape[-1] == 3
+    got = VO.preprocess_frames(frames, 288, mode)
+    assert got.dtype == want.dtype == np.float32 and got.shape == want.shape == (16, 288, 288, 3)
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError, match="frames"):
+        video_utils.read_frames(REF_MP4, 10 ** 6)
+
+
 def test_normalisation_and_errors():
     frames = np.random.default_rng(0).integers(0, 256, (3, 40, 64, 3)).astype(np.uint8)
     out = VO.preprocess_frames(frames, 36, "center_crop")
