@@ -164,7 +164,28 @@ def full_size_cases():
          text_emb_raw=np.asarray(te_raw), ids=ids, paddings=pad)
 
 
+def large_cases():
+    # BASELINE.json configs[2] / [4]: the large models (24 + 4 blocks, D = 1024, 16 heads, temporal table 8 -> 16 frames,
+    # bilinear up-sampling) through models.get_model: encoder on 1 clip, video-text model on 1 clip + 3 queries
+    name = "videoprism_public_v1_large"
+    W = tree_of(O.make_synthetic_weights(O.CONFIGS[name]))
+    v = O.make_video(1, 16, 288, seed=5)
+    out, _ = models.get_model(name).apply(W, jnp.asarray(v), train=False)
+    out = np.asarray(out)
+    save("large_config3", features_sample=out[:, ::TOKEN_STRIDE], checksum=summarise(out), token_stride=np.array(TOKEN_STRIDE))
+    del W
+    name = "videoprism_lvt_public_v1_large"
+    W = tree_of(O.make_synthetic_weights(O.CONFIGS[name]))
+    v = O.make_video(1, 16, 288, seed=6)
+    ids, pad = O.make_text(3)
+    ve, te, _ = models.get_model(name).apply(W, jnp.asarray(v), jnp.asarray(ids), jnp.asarray(pad), train=False)
+    save("lvt_large_1clip_3text", video_emb=np.asarray(ve), text_emb=np.asarray(te), ids=ids, paddings=pad)
+
+
 if __name__ == "__main__":
+    if "--large-only" in sys.argv:
+        large_cases()
+        sys.exit(0)
     if "--classifier-only" in sys.argv:
         classifier_case()
         sys.exit(0)
@@ -177,3 +198,4 @@ if __name__ == "__main__":
     tiny_cases()
     if "--tiny-only" not in sys.argv:
         full_size_cases()
+        large_cases()

@@ -122,3 +122,19 @@ def test_lvt_base_one_clip_three_queries():
     assert np.abs(ve - g["video_emb"]).max() <= EMB_TOL and np.abs(te - g["text_emb"]).max() <= EMB_TOL
     # the verify script's own criterion (verify_clip_models.py:92-95): cosine-similarity matrix within 1e-3
     assert np.abs(ve @ te.T - g["video_emb"] @ g["text_emb"].T).max() < 1e-3
+
+
+def test_large_models_full_size():
+    """BASELINE.json configs[2] / [4] models (large: 24 + 4 blocks, D = 1024, temporal table 8 -> 16) against goldens made by
+    the reference's own code through models.get_model."""
+    g = load("large_config3")
+    cfg = O.CONFIGS["videoprism_public_v1_large"]
+    out, _ = O.run_encoder(cfg, O.make_synthetic_weights(cfg), O.make_video(1, 16, 288, seed=5))
+    stride = int(g["token_stride"])
+    assert np.abs(out[:, ::stride] - g["features_sample"]).max() <= FEAT_TOL
+    x = out.astype(np.float64)
+    np.testing.assert_allclose(np.array([np.abs(x).sum(), (x * x).sum()]), g["checksum"][1:], rtol=1e-5)
+    g = load("lvt_large_1clip_3text")
+    cfg = O.CONFIGS["videoprism_lvt_public_v1_large"]
+    ve, te, _ = O.run_clip(cfg, O.make_synthetic_weights(cfg), O.make_video(1, 16, 288, seed=6), g["ids"], g["paddings"])
+    assert np.abs(ve - g["video_emb"]).max() <= EMB_TOL and np.abs(te - g["text_emb"]).max() <= EMB_TOL

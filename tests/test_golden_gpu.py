@@ -148,3 +148,21 @@ def test_tiny_clip_primer_hybrid_text_tower(fuse_ln, monkeypatch):
     check("primer clip text_emb", te, g["text_emb"])
     _, te_raw, _ = m.apply(W, None, g["ids"], g["paddings"], train=False, normalize=False)
     check("primer clip text_emb (raw)", te_raw, g["text_emb_raw"])
+
+
+def test_large_models_full_size():
+    """The large encoder (BASELINE configs[2]) and the large video-text model (configs[4]) against reference-generated goldens."""
+    import videoprism_b200 as vp
+    g = np.load(os.path.join(G, "large_config3.npz"))
+    name = "videoprism_public_v1_large"
+    m = vp.get_model(name)
+    out, _ = m.apply(O.make_synthetic_weights(O.CONFIGS[name]), O.make_video(1, 16, 288, seed=5), train=False)
+    check("large encoder vs reference golden", out[:, ::int(g["token_stride"])], g["features_sample"])
+    del m
+    g = np.load(os.path.join(G, "lvt_large_1clip_3text.npz"))
+    name = "videoprism_lvt_public_v1_large"
+    m = vp.get_model(name)
+    ve, te, _ = m.apply(O.make_synthetic_weights(O.CONFIGS[name]), O.make_video(1, 16, 288, seed=6), g["ids"], g["paddings"], train=False)
+    check("lvt large video_emb vs reference golden", ve, g["video_emb"])
+    check("lvt large text_emb vs reference golden", te, g["text_emb"])
+    assert np.abs(ve @ te.T - g["video_emb"] @ g["text_emb"].T).max() < 1e-3      # verify_clip_models.py:92-95
