@@ -1214,6 +1214,7 @@ int64_t vp_kernel_launches(const vp_handle* h) { return h ? h->launches : 0; }
 // aggregates the event-to-event times by label ("label count total_ms" per line, then "TOTAL n ms").
 int vp_trace(vp_handle* h, int enable) {
   if (h == nullptr) return VP_ERR_INVALID;
+  DeviceScope device_scope(h->device);
   for (auto& t : h->trace) cudaEventDestroy(t.second);
   h->trace.clear();
   h->trace_on = enable != 0;
