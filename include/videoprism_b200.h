@@ -79,6 +79,15 @@ VP_API int vp_create(const vp_config* cfg, vp_handle** out);   /* on the calling
  * workspace and every kernel it launches live on `device`; all buffers passed to its entry points must too. */
 VP_API int vp_create_on_device(const vp_config* cfg, int device, vp_handle** out);
 VP_API int vp_handle_device(const vp_handle* h);                /* device ordinal the handle is bound to */
+/* fp32 CHECK MODE.  models.get_model(name) computes in float32 unless fprop_dtype says otherwise (videoprism/layers.py:182-205);
+ * the production path of this library computes on the bf16 tensor cores.  A handle created with VP_FLAG_CHECK_FP32 (or any
+ * handle of a process started with VP_CHECK_FP32=1) runs the SAME entry points entirely in float32 on the CUDA cores: fp32
+ * residual stream, LayerNorm output, GEMM operands / accumulators, softmax and P.  It is ~50x slower and exists to hold the
+ * implementation to the reference's own fp32 envelope (max-abs <= 1e-3 on features, <= 1e-5 on normalised embeddings:
+ * FLAX_TO_MLX_CONVERSION_GUIDE.md:321-358, verify_clip_models.py:92-95).  Supports norm_policy 'pre' (every released model). */
+#define VP_FLAG_CHECK_FP32 1u
+VP_API int vp_create_ex(const vp_config* cfg, int device, unsigned flags, vp_handle** out);
+VP_API int vp_handle_flags(const vp_handle* h);
 VP_API void vp_destroy(vp_handle* h);
 VP_API const char* vp_last_error(const vp_handle* h); /* h may be NULL: last error of a failed vp_create */
 

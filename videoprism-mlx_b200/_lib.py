@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libvideoprism_b200.so")
 VP_OK, VP_ERR_INVALID, VP_ERR_KEY, VP_ERR_INCOMPLETE, VP_ERR_CUDA, VP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 VP_F32, VP_BF16, VP_I32, VP_U8 = 0, 1, 2, 3
 VP_KIND_ENCODER, VP_KIND_CLIP, VP_KIND_CLASSIFIER = 0, 1, 2
+VP_FLAG_CHECK_FP32 = 1
 
 
 class VpConfig(C.Structure):
@@ -28,6 +29,8 @@ _I = C.c_int
 _PROTOS = {
     "vp_create": (_I, [C.POINTER(VpConfig), C.POINTER(_P)]),
     "vp_create_on_device": (_I, [C.POINTER(VpConfig), _I, C.POINTER(_P)]),
+    "vp_create_ex": (_I, [C.POINTER(VpConfig), _I, C.c_uint, C.POINTER(_P)]),
+    "vp_handle_flags": (_I, [_P]),
     "vp_handle_device": (_I, [_P]),
     "vp_destroy": (None, [_P]),
     "vp_last_error": (C.c_char_p, [_P]),

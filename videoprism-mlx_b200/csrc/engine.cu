@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/videoprism_b200.h"
+#include "check_fp32.h"
 #include "kernels.h"
 
 namespace vp {
@@ -42,14 +43,18 @@ std::string g_create_error;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  cudaError_t ensure(size_t n, bool zero = false) {
+  // Grows (never shrinks) the buffer.  cudaFree / cudaMalloc synchronise with the device, so a buffer still in use by
+  // queued work is never pulled away; `zero` clears a NEW allocation on the caller's stream `st`, i.e. ordered before
+  // the kernels the caller enqueues next on that stream (a memset on the legacy default stream would not be ordered
+  // against cudaStreamNonBlocking streams).
+  cudaError_t ensure(size_t n, bool zero = false, cudaStream_t st = nullptr) {
     if (n <= bytes) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; bytes = 0;
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) return e;
     bytes = n;
-    if (zero) e = cudaMemset(p, 0, n);
+    if (zero) e = cudaMemsetAsync(p, 0, n, st);
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -69,6 +74,9 @@ struct StackWeights {
   // attention / FFN outputs pass through these 'post_layer_norm's before the residual add
   bool primer = false;
   float *lnp1_g = nullptr, *lnp1_b = nullptr, *lnp2_g = nullptr, *lnp2_b = nullptr;
+  // fp32 check mode only (check_fp32.cu): the two projections that are otherwise kept in bf16 alone.  post.w [L][D_out][D] is
+  // [N, K]; ffn_layer2 kernel [L][F][D] is [K, N].  (q/k/v and ffn_layer1 use the f_* copies above.)
+  float *c_wo = nullptr, *c_w2 = nullptr;
 };
 
 struct ParamSpec {
@@ -111,6 +119,10 @@ struct vp_handle {
   StackWeights spatial, temporal, aux, text;
   std::vector<StackWeights*> stacks;   // the stacks this model has (for finalize_stack)
   bool fuse_ln = true;                 // LayerNorm folded into the QKV / FFN1 GEMMs (VP_FUSE_LN=0 disables)
+  bool check_fp32 = false;             // VP_FLAG_CHECK_FP32: the whole forward in float32 on the CUDA cores (check_fp32.cu)
+  float* c_wpatch = nullptr;           // check mode: patch projection kernel [k_patch, D] fp32
+  float *c_pool_wkq = nullptr, *c_pool_wv = nullptr, *c_pool_wpost = nullptr;   // [D, H] / [D, H*ph] / [D, H*ph] fp32
+  DevBuf c_x, c_n, c_qkv, c_u, c_patch, c_pool;                                   // fp32 workspace
   float *sp_ln_g = nullptr, *sp_ln_b = nullptr, *tp_ln_g = nullptr, *tp_ln_b = nullptr;
   // pooler (collapsed single-query form, see finalize_pooler)
   std::vector<float> h_pool_query, h_pool_wq, h_pool_bq, h_pool_wk, h_pool_pds;
@@ -204,6 +216,10 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
   if ((e = dev_alloc(h, &w->f_bqkv, (size_t)L * 3 * D)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &w->f_w1, (size_t)L * D * F)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &w->f_b1, (size_t)L * F)) != cudaSuccess) return e;
+  if (h->check_fp32) {
+    if ((e = dev_alloc(h, &w->c_wo, (size_t)L * D * D)) != cudaSuccess) return e;
+    if ((e = dev_alloc(h, &w->c_w2, (size_t)L * F * D)) != cudaSuccess) return e;
+  }
   if (primer) {
     if ((e = dev_alloc(h, &w->lnp1_g, (size_t)L * D)) != cudaSuccess) return e;
     if ((e = dev_alloc(h, &w->lnp1_b, (size_t)L * D)) != cudaSuccess) return e;
@@ -253,6 +269,7 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
   }
   // post.w is [D_out, (H dh)]: already the K-major [N, K] layout the GEMM wants (layers.py:483).
   add_spec(h, p + "/self_attention/post/w", {L, D, H, dh}, [ww, L, D](const float* s, cudaStream_t st) {
+    if (ww.c_wo != nullptr) { cudaError_t e = copy_f32(s, ww.c_wo, (size_t)L * D * D, st); if (e != cudaSuccess) return e; }
     return vp::launch_cast_bf16(st, s, ww.wo, (size_t)L * D * D, 1.0f); });
   add_spec(h, p + "/self_attention/post/b", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return copy_f32(s, ww.bo, (size_t)L * D, st); });
@@ -281,7 +298,7 @@ cudaError_t add_stack(vp_handle* h, const std::string& prefix, StackWeights* w, 
       cudaError_t e = vp::launch_transpose_cast(st, s + (size_t)l * F * D, ww.w2 + (size_t)l * D * F, F, D, F, 1.0f);
       if (e != cudaSuccess) return e;
     }
-    return cudaSuccess; });
+    return ww.c_w2 != nullptr ? copy_f32(s, ww.c_w2, (size_t)L * F * D, st) : cudaSuccess; });
   add_spec(h, p + "/ff_layer/ffn_layer2/linear/bias", {L, D}, [ww, L, D](const float* s, cudaStream_t st) {
     return copy_f32(s, ww.b2, (size_t)L * D, st); });
   return cudaSuccess;
@@ -313,7 +330,9 @@ cudaError_t add_encoder(vp_handle* h, const std::string& prefix) {
   if ((e = dev_alloc(h, &h->w_patch, (size_t)D * h->k_patch_pad)) != cudaSuccess) return e;
   if ((e = dev_alloc(h, &h->b_patch, D)) != cudaSuccess) return e;
   vp_handle* hh = h;
+  if (h->check_fp32 && (e = dev_alloc(h, &h->c_wpatch, (size_t)h->k_patch * D)) != cudaSuccess) return e;
   add_spec(h, prefix + "/patch_projection/linear/kernel", {h->k_patch, D}, [hh, D](const float* s, cudaStream_t st) {
+    if (hh->c_wpatch != nullptr) { cudaError_t e = copy_f32(s, hh->c_wpatch, (size_t)hh->k_patch * D, st); if (e != cudaSuccess) return e; }
     return vp::launch_transpose_cast(st, s, hh->w_patch, hh->k_patch, D, hh->k_patch_pad, 1.0f); });
   add_spec(h, prefix + "/patch_projection/linear/bias", {D}, [hh, D](const float* s, cudaStream_t st) {
     return copy_f32(s, hh->b_patch, D, st); });
@@ -347,10 +366,17 @@ cudaError_t add_pooler(vp_handle* h, const std::string& pp, int ph) {
   add_spec(h, pp + "/pooling_attention/key/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_wk, s, (size_t)D * H * ph, st); });
   // key bias shifts every score of a head by the same constant -> cancels in the softmax; accepted, unused.
   add_spec(h, pp + "/pooling_attention/key/b", {H, ph}, [](const float*, cudaStream_t) { return cudaSuccess; });
+  if (h->check_fp32) {
+    if ((e = dev_alloc(h, &h->c_pool_wkq, (size_t)D * H)) != cudaSuccess) return e;
+    if ((e = dev_alloc(h, &h->c_pool_wv, (size_t)D * H * ph)) != cudaSuccess) return e;
+    if ((e = dev_alloc(h, &h->c_pool_wpost, (size_t)D * H * ph)) != cudaSuccess) return e;
+  }
   add_spec(h, pp + "/pooling_attention/value/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) {
+    if (hh->c_pool_wv != nullptr) { cudaError_t e = copy_f32(s, hh->c_pool_wv, (size_t)D * H * ph, st); if (e != cudaSuccess) return e; }
     return vp::launch_cast_bf16(st, s, hh->pool_wv, (size_t)D * H * ph, 1.0f); });  // kept [D, (H dh)]: pool_ctx_kernel reads it j-contiguous
   add_spec(h, pp + "/pooling_attention/value/b", {H, ph}, [hh, H, ph](const float* s, cudaStream_t st) { return copy_f32(s, hh->pool_bv, (size_t)H * ph, st); });
   add_spec(h, pp + "/pooling_attention/post/w", {D, H, ph}, [hh, D, H, ph](const float* s, cudaStream_t st) {
+    if (hh->c_pool_wpost != nullptr) { cudaError_t e = copy_f32(s, hh->c_pool_wpost, (size_t)D * H * ph, st); if (e != cudaSuccess) return e; }
     return vp::launch_cast_bf16(st, s, hh->pool_wpost, (size_t)D * H * ph, 1.0f); });
   add_spec(h, pp + "/pooling_attention/post/b", {D}, [hh, D](const float* s, cudaStream_t st) { return copy_f32(s, hh->pool_bpost, D, st); });
   add_spec(h, pp + "/pooling_attention/per_dim_scale/per_dim_scale", {ph}, [hh, ph](const float* s, cudaStream_t st) { return host_copy(&hh->h_pool_pds, s, ph, st); });
@@ -512,8 +538,14 @@ int finalize_pooler(vp_handle* h) {
       hl[(size_t)(H + hh) * D + d] = __float2bfloat16(w - __bfloat162float(hi));
     }
   CK(cudaMemcpy(h->pool_wkq, hl.data(), hl.size() * sizeof(bf16), cudaMemcpyHostToDevice));
-  h->h_pool_wq.clear(); h->h_pool_wq.shrink_to_fit();
-  h->h_pool_wk.clear(); h->h_pool_wk.shrink_to_fit();
+  if (h->c_pool_wkq != nullptr) {   // check mode: the folded score weights in fp32, [D, H]
+    std::vector<float> t((size_t)D * H);
+    for (int hh = 0; hh < H; ++hh)
+      for (int d = 0; d < D; ++d) t[(size_t)d * H + hh] = wkq[(size_t)hh * D + d];
+    CK(cudaMemcpy(h->c_pool_wkq, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // the host copies of the query / key projections stay for the life of the handle (like f_wqkv / f_w1): vp_finalize
+  // re-folds them after any later vp_set_weight, whichever leaf changed
   return VP_OK;
 }
 
@@ -641,6 +673,154 @@ int ensure_workspace(vp_handle* h, size_t M, int D, int F) {
   return VP_OK;
 }
 
+// ===================================================================== fp32 check mode (check_fp32.cu)
+// The same forward, as the reference writes it, entirely in float32: x (residual stream), LayerNorm output, q/k/v,
+// attention context and the FFN hidden layer are fp32 buffers; every GEMM is an fp32 FFMA GEMM on the fp32 weights.
+int ensure_workspace_f32(vp_handle* h, size_t M, int D, int F) {
+  CK(h->c_x.ensure(M * D * sizeof(float)));
+  CK(h->c_n.ensure(M * D * sizeof(float)));
+  CK(h->c_qkv.ensure(M * 3 * D * sizeof(float)));
+  CK(h->c_u.ensure(M * F * sizeof(float)));
+  return VP_OK;
+}
+
+// One 'pre'-LayerNorm Transformer stack (layers.py:797-872, :989-1041) over the fp32 residual stream x [M, D], in place.
+int run_stack_f32(vp_handle* h, const StackWeights& w, float* x, int M, const SeqLayout& sl, int act, cudaStream_t st,
+                  const char* const* tag) {
+  if (w.primer) return h->fail(VP_ERR_UNSUPPORTED, "fp32 check mode supports norm_policy 'pre' only");
+  const int D = w.D, F = w.F, H = w.H;
+  float* n = static_cast<float*>(h->c_n.p);
+  float* qkv = static_cast<float*>(h->c_qkv.p);
+  float* u = static_cast<float*>(h->c_u.p);
+  const float qscale = 1.0f / sqrtf(static_cast<float>(D / H));   // layers.py:569-584 (a power of two for dh = 64: exact)
+  for (int l = 0; l < w.L; ++l) {
+    vp::f32::LayerNorm ln;
+    ln.x = x; ln.ldx = D; ln.gamma1 = w.ln1_g + (size_t)l * D; ln.beta = w.ln1_b + (size_t)l * D; ln.y = n; ln.ldy = D; ln.M = M; ln.D = D;
+    CK(vp::f32::layernorm(st, ln)); h->mark(st, tag[0]);
+    for (int i = 0; i < 3; ++i) {   // query / key / value projections (layers.py:486-498), w [D, (N H)] = [K, N]
+      vp::f32::Sgemm g;
+      g.A = n; g.lda = D; g.W = w.f_wqkv + ((size_t)l * 3 + i) * D * D; g.ldw = D; g.C = qkv + (size_t)i * D; g.ldc = 3 * D;
+      g.M = M; g.N = D; g.K = D; g.bias = w.f_bqkv + ((size_t)l * 3 + i) * D; g.alpha = i == 0 ? qscale : 1.0f;
+      CK(vp::f32::sgemm(st, g)); h->mark(st, tag[1]);
+    }
+    vp::f32::Attention at;
+    at.q = qkv; at.k = qkv + D; at.v = qkv + 2 * D; at.ld = 3 * D; at.out = n; at.ldo = D;
+    at.num_seq = sl.num_seq; at.S = sl.S; at.group = sl.group; at.heads = H; at.dh = D / H;
+    at.cap = h->cfg.atten_logit_cap; at.key_pad = sl.key_pad; at.causal = sl.causal;
+    CK(vp::f32::attention(st, at)); h->mark(st, tag[2]);
+    {   // post projection + residual (layers.py:483-498, :855); post.w [D_out, (N H)] = [N, K]
+      vp::f32::Sgemm g;
+      g.A = n; g.lda = D; g.W = w.c_wo + (size_t)l * D * D; g.ldw = D; g.w_nk = 1; g.C = x; g.ldc = D; g.M = M; g.N = D; g.K = D;
+      g.bias = w.bo + (size_t)l * D; g.resid = x; g.ldr = D;
+      CK(vp::f32::sgemm(st, g)); h->mark(st, tag[3]);
+    }
+    ln.gamma1 = w.ln2_g + (size_t)l * D; ln.beta = w.ln2_b + (size_t)l * D;
+    CK(vp::f32::layernorm(st, ln)); h->mark(st, tag[0]);
+    {   // ffn_layer1 + activation, zeroed on padded tokens (layers.py:391-398)
+      vp::f32::Sgemm g;
+      g.A = n; g.lda = D; g.W = w.f_w1 + (size_t)l * D * F; g.ldw = F; g.C = u; g.ldc = F; g.M = M; g.N = F; g.K = D;
+      g.bias = w.f_b1 + (size_t)l * F; g.act = act; g.row_scale = sl.row_scale;
+      CK(vp::f32::sgemm(st, g)); h->mark(st, tag[4]);
+    }
+    {   // ffn_layer2, zeroed on padded tokens, + residual (layers.py:402-425)
+      vp::f32::Sgemm g;
+      g.A = u; g.lda = F; g.W = w.c_w2 + (size_t)l * F * D; g.ldw = D; g.C = x; g.ldc = D; g.M = M; g.N = D; g.K = F;
+      g.bias = w.b2 + (size_t)l * D; g.row_scale = sl.row_scale; g.resid = x; g.ldr = D;
+      CK(vp::f32::sgemm(st, g)); h->mark(st, tag[5]);
+    }
+  }
+  return VP_OK;
+}
+
+// fp32 counterpart of encoder_body: leaves LN_temporal(x) (final_ln_in_place) or the pre-LN stream in c_x.
+int encoder_body_f32(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
+                     bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, P = c.patch_size;
+  if (B <= 0 || T <= 0) return h->fail(VP_ERR_INVALID, "empty batch (B=%d, T=%d)", B, T);
+  if (H != W) return h->fail(VP_ERR_INVALID, "H (%d) must equal W (%d) (encoders.py:435)", H, W);
+  if (H % P || W % P) return h->fail(VP_ERR_INVALID, "Image height (%d) and width (%d) should be multiples of patch_size (%d)", H, W, P);
+  const int gh = H / P, gw = W / P, N = gh * gw;
+  const size_t M = (size_t)B * T * N;
+  if (M > 0x7fffffffULL / (size_t)(3 * D > c.mlp_dim ? 3 * D : c.mlp_dim)) return h->fail(VP_ERR_INVALID, "batch too large");
+  int rc;
+  if ((rc = prepare_pos_tables(h, T, gh, gw, st)) != VP_OK) return rc;
+  if ((rc = ensure_workspace_f32(h, M, D, c.mlp_dim)) != VP_OK) return rc;
+  CK(h->c_patch.ensure(M * h->k_patch * sizeof(float)));
+  float* x = static_cast<float*>(h->c_x.p);
+  float* patches = static_cast<float*>(h->c_patch.p);
+  const float *pad_tok = nullptr, *keep_tok = nullptr, *pad_tube = nullptr;
+  if (frame_pad != nullptr) {
+    CK(h->ws_misc.ensure(3 * M * sizeof(float)));
+    float* base = static_cast<float*>(h->ws_misc.p);
+    CK(vp::launch_pad_expand(st, frame_pad, base, base + M, base + 2 * M, B, T, N)); h->mark(st, "pad_expand");
+    pad_tok = base; keep_tok = base + M; pad_tube = base + 2 * M;
+  }
+  h->mark(st, nullptr, false);
+  CK(vp::f32::patchify(st, video, in_dtype == VP_U8, patches, B * T, H, W, P)); h->mark(st, "patchify");
+  {   // patch projection + spatial position table (encoders.py:488-514)
+    vp::f32::Sgemm g;
+    g.A = patches; g.lda = h->k_patch; g.W = h->c_wpatch; g.ldw = D; g.C = x; g.ldc = D; g.M = (int)M; g.N = D; g.K = h->k_patch;
+    g.bias = h->b_patch; g.pos_table = h->d_spatial_pos; g.pos_period = N;
+    CK(vp::f32::sgemm(st, g)); h->mark(st, "patch_proj");
+  }
+  SeqLayout sp{B * T, N, 1, 0, pad_tok, keep_tok, 1};
+  if ((rc = run_stack_f32(h, h->spatial, x, (int)M, sp, vp::ACT_GELU, st, kTagSpatial)) != VP_OK) return rc;
+  {   // spatial_ln (+ temporal position table, encoders.py:528-553), in place
+    vp::f32::LayerNorm ln;
+    ln.x = x; ln.ldx = D; ln.gamma1 = h->sp_ln_g; ln.beta = h->sp_ln_b; ln.y = x; ln.ldy = D; ln.y2 = spatial_f32;
+    ln.add_table = h->d_temporal_pos; ln.add_div = N; ln.add_mod = T; ln.M = (int)M; ln.D = D;
+    CK(vp::f32::layernorm(st, ln)); h->mark(st, "spatial_ln");
+  }
+  SeqLayout tp{B * N, T, N, 0, pad_tube, keep_tok};
+  if ((rc = run_stack_f32(h, h->temporal, x, (int)M, tp, vp::ACT_GELU, st, kTagTemporal)) != VP_OK) return rc;
+  {   // temporal_ln (encoders.py:567-569)
+    vp::f32::LayerNorm ln;
+    ln.x = x; ln.ldx = D; ln.gamma1 = h->tp_ln_g; ln.beta = h->tp_ln_b; ln.M = (int)M; ln.D = D;
+    float* tmp = static_cast<float*>(h->c_n.p);
+    if (final_ln_in_place) { ln.y = x; ln.ldy = D; ln.y2 = out_f32; }
+    else if (out_f32 != nullptr) { ln.y = out_f32; ln.ldy = D; }
+    else { ln.y = tmp; ln.ldy = D; }
+    CK(vp::f32::layernorm(st, ln)); h->mark(st, "temporal_ln");
+    if (!final_ln_in_place && out_f32 == nullptr && out_bf16 != nullptr) { CK(vp::f32::cast_to_bf16(st, tmp, out_bf16, M * D)); h->mark(st, "cast_bf16"); }
+  }
+  if (M_out) *M_out = M;
+  return VP_OK;
+}
+
+// Pooling head in fp32 (layers.py:1044-1136) on x [num_seq, S, D] -> out [num_seq, D] (+ optional l2 normalisation).
+int pool_f32(vp_handle* h, const float* x, int num_seq, int S, int normalize, float* out, cudaStream_t st) {
+  const vp_config& c = h->cfg;
+  const int D = c.model_dim, H = c.num_heads, ph = h->pool_ph, HP = H * ph;
+  const size_t n = (size_t)num_seq;
+  const size_t o_scores = 0, o_xbar = o_scores + n * S * H, o_ctx = o_xbar + n * H * D, o_y = o_ctx + n * HP, o_ln = o_y + n * D, o_end = o_ln + n * D;
+  CK(h->c_pool.ensure(o_end * sizeof(float)));
+  float* base = static_cast<float*>(h->c_pool.p);
+  float *scores = base + o_scores, *xbar = base + o_xbar, *ctx = base + o_ctx, *y = base + o_y, *yln = base + o_ln;
+  {   // scores[s, h] = x[s] . wkq[:, h]  (key bias and the constant part cancel in the softmax)
+    vp::f32::Sgemm g;
+    g.A = x; g.lda = D; g.W = h->c_pool_wkq; g.ldw = H; g.C = scores; g.ldc = H; g.M = num_seq * S; g.N = H; g.K = D;
+    CK(vp::f32::sgemm(st, g)); h->mark(st, "pooler.scores");
+  }
+  CK(vp::f32::pool(st, x, scores, xbar, num_seq, S, D, H)); h->mark(st, "pooler.accum");
+  for (int hh = 0; hh < H; ++hh) {   // value projection of the pooled token, per head: [num_seq, D] x [D, ph]
+    vp::f32::Sgemm g;
+    g.A = xbar + (size_t)hh * D; g.lda = H * D; g.W = h->c_pool_wv + (size_t)hh * ph; g.ldw = HP; g.C = ctx + (size_t)hh * ph; g.ldc = HP;
+    g.M = num_seq; g.N = ph; g.K = D; g.bias = h->pool_bv + (size_t)hh * ph;
+    CK(vp::f32::sgemm(st, g)); h->mark(st, "pooler.value");
+  }
+  {   // post projection: post.w [D, (H ph)] = [N, K]
+    vp::f32::Sgemm g;
+    g.A = ctx; g.lda = HP; g.W = h->c_pool_wpost; g.ldw = HP; g.w_nk = 1; g.C = y; g.ldc = D; g.M = num_seq; g.N = D; g.K = HP; g.bias = h->pool_bpost;
+    CK(vp::f32::sgemm(st, g)); h->mark(st, "pooler.post");
+  }
+  vp::f32::LayerNorm ln;
+  ln.x = y; ln.ldx = D; ln.gamma1 = h->pool_ln_g; ln.beta = h->pool_ln_b; ln.y = normalize ? yln : out; ln.ldy = D; ln.M = num_seq; ln.D = D;
+  CK(vp::f32::layernorm(st, ln)); h->mark(st, "pooler.ln");
+  if (normalize) { CK(vp::launch_l2norm(st, yln, out, num_seq, D)); h->mark(st, "pooler.l2norm"); }
+  return VP_OK;
+}
+
 // Selects the handle's device for the duration of one C-ABI call and restores the caller's current device afterwards: an
 // entry point must not change the calling thread's device as a side effect (a destructor running vp_destroy for a model
 // on cuda:0 would otherwise silently move the caller off cuda:1).
@@ -670,6 +850,7 @@ int check_ready(vp_handle* h) {   // callers hold a DeviceScope on h->device
 // writes LN outputs where requested.  Returns the token count through *M_out.
 int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
                  bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
+  if (h->check_fp32) return encoder_body_f32(h, video, in_dtype, B, T, H, W, frame_pad, out_f32, out_bf16, final_ln_in_place, spatial_f32, st, M_out);
   const vp_config& c = h->cfg;
   const int D = c.model_dim, P = c.patch_size;
   if (B <= 0 || T <= 0) return h->fail(VP_ERR_INVALID, "empty batch (B=%d, T=%d)", B, T);
@@ -681,7 +862,7 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
   int rc;
   if ((rc = prepare_pos_tables(h, T, gh, gw, st)) != VP_OK) return rc;
   if ((rc = ensure_workspace(h, M, D, c.mlp_dim)) != VP_OK) return rc;
-  CK(h->ws_patch.ensure(M * h->k_patch_pad * sizeof(bf16), /*zero=*/true));
+  CK(h->ws_patch.ensure(M * h->k_patch_pad * sizeof(bf16), /*zero=*/true, st));   // the K padding columns stay zero
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   bf16* patches = static_cast<bf16*>(h->ws_patch.p);
 
@@ -742,10 +923,20 @@ extern "C" {
 
 int vp_create(const vp_config* cfg, vp_handle** out) { return vp_create_on_device(cfg, -1, out); }
 
+int vp_create_on_device(const vp_config* cfg, int device, vp_handle** out) {
+  // VP_CHECK_FP32=1 turns every handle of the process into a check-mode handle (the switch the parity tests use)
+  const char* ev = getenv("VP_CHECK_FP32");
+  return vp_create_ex(cfg, device, (ev && atoi(ev) != 0) ? VP_FLAG_CHECK_FP32 : 0, out);
+}
+
+int vp_handle_flags(const vp_handle* h) { return h ? (h->check_fp32 ? VP_FLAG_CHECK_FP32 : 0) : 0; }
+
 int vp_handle_device(const vp_handle* h) { return h ? h->device : -1; }
 
-int vp_create_on_device(const vp_config* cfg, int device, vp_handle** out) {
+int vp_create_ex(const vp_config* cfg, int device, unsigned flags, vp_handle** out) {
   if (out == nullptr || cfg == nullptr) { g_create_error = "null argument"; return VP_ERR_INVALID; }
+  if (flags & ~static_cast<unsigned>(VP_FLAG_CHECK_FP32)) { g_create_error = "unknown flag"; return VP_ERR_INVALID; }
+  if ((flags & VP_FLAG_CHECK_FP32) && cfg->text_norm_policy != 0) { g_create_error = "fp32 check mode supports norm_policy 'pre' only"; return VP_ERR_UNSUPPORTED; }
   *out = nullptr;
   if (cfg->model_dim <= 0 || cfg->num_heads <= 0 || cfg->model_dim % cfg->num_heads || cfg->patch_size <= 0 ||
       (cfg->patch_size % 2) || cfg->mlp_dim <= 0 || (cfg->model_dim % 8) || (cfg->mlp_dim % 8)) {
@@ -771,6 +962,7 @@ int vp_create_on_device(const vp_config* cfg, int device, vp_handle** out) {
   DeviceScope device_scope(device);   // cudaSetDevice also creates the primary context if this is the device's first use
   vp_handle* h = new vp_handle();
   h->cfg = *cfg;
+  h->check_fp32 = (flags & VP_FLAG_CHECK_FP32) != 0;
   if (const char* ev = getenv("VP_HOST_CHUNK_CLIPS")) h->host_chunk_clips = atoi(ev);   // tuning knob of the host pipeline
   if (const char* ev = getenv("VP_FUSE_LN")) h->fuse_ln = atoi(ev) != 0;
   if (cudaGetDevice(&h->device) != cudaSuccess || h->device != device) {
@@ -812,7 +1004,8 @@ void vp_destroy(vp_handle* h) {
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_comp[i]); cudaEventDestroy(h->ev_out[i]); }
     cudaEventDestroy(h->ev_start);
   }
-  DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats};
+  DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats,
+                    &h->c_x, &h->c_n, &h->c_qkv, &h->c_u, &h->c_patch, &h->c_pool};
   for (DevBuf* b : bufs) b->release();
   delete h;
 }
@@ -1044,6 +1237,17 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   // stream of the auxiliary encoder, so LN writes bf16 back into ws_x.
   rc = encoder_body(h, video, VP_F32, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
   if (rc != VP_OK) return rc;
+  if (h->check_fp32) {   // the same three stages in float32
+    float* xf = static_cast<float*>(h->c_x.p);
+    const int Nf = (int)(M / ((size_t)B * T));
+    if (c.num_auxiliary_layers > 0) {
+      SeqLayout ax{B, T * Nf, 1, 0, nullptr, nullptr};
+      if ((rc = run_stack_f32(h, h->aux, xf, (int)M, ax, vp::ACT_GELU, st, kTagAux)) != VP_OK) return rc;
+    }
+    if ((rc = pool_f32(h, xf, B, T * Nf, normalize, video_emb, st)) != VP_OK) return rc;
+    if (frame_embeddings && (rc = pool_f32(h, xf, B * T, Nf, normalize, frame_embeddings, st)) != VP_OK) return rc;
+    return VP_OK;
+  }
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   const int N = (int)(M / ((size_t)B * T));
   if (c.num_auxiliary_layers > 0) {  // auxiliary_encoder: full attention over all T*N tokens of a clip (:846-857)
@@ -1081,6 +1285,14 @@ int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H,
   // encoder (encoders.py:616-627); the pooler reads LN(x) in bf16 from the residual buffer
   rc = encoder_body(h, video, VP_F32, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
   if (rc != VP_OK) return rc;
+  if (h->check_fp32) {
+    const int Nf = (int)(M / ((size_t)B * T));
+    CK(h->ws_pool.ensure((size_t)B * D * sizeof(float)));
+    float* embf = global_embeddings ? global_embeddings : static_cast<float*>(h->ws_pool.p);
+    if ((rc = pool_f32(h, static_cast<const float*>(h->c_x.p), B, T * Nf, 0, embf, st)) != VP_OK) return rc;
+    CK(vp::launch_dense_f32(st, embf, h->cls_w, h->cls_b, logits, B, D, c.num_classes)); h->mark(st, "classifier_projection");
+    return VP_OK;
+  }
   const bf16* x = static_cast<const bf16*>(h->ws_x.p);
   const int N = (int)(M / ((size_t)B * T));
   const int ph = h->pool_ph;
@@ -1109,11 +1321,26 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
   const int D = c.model_dim, S = L + 1;
   const size_t M = (size_t)Q * S;
   if ((rc = prepare_pe(h, L, st)) != VP_OK) return rc;
-  if ((rc = ensure_workspace(h, M, D, 4 * D)) != VP_OK) return rc;
   const size_t Mp = (M + 63) & ~static_cast<size_t>(63);  // keeps the sub-buffers 16-byte aligned (float4 stores)
   CK(h->ws_misc.ensure((2 * Mp + (size_t)Q * D) * sizeof(float)));
   float* keep = static_cast<float*>(h->ws_misc.p);
   float* pad_ext = keep + Mp;
+  if (h->check_fp32) {   // the text tower in float32 (encoders.py:656-759)
+    if ((rc = ensure_workspace_f32(h, M, D, 4 * D)) != VP_OK) return rc;
+    float* xf = static_cast<float*>(h->c_x.p);
+    h->mark(st, nullptr, false);
+    CK(vp::f32::text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, xf, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->mark(st, "text.embed");
+    SeqLayout tlf{Q, S, 1, 1, pad_ext, keep};
+    if ((rc = run_stack_f32(h, h->text, xf, (int)M, tlf, vp::ACT_RELU, st, kTagText)) != VP_OK) return rc;
+    float* tmpf = static_cast<float*>(h->ws_misc.p) + 2 * Mp;
+    vp::f32::LayerNorm lnf;   // unimodal_ln on the class token only (features[:, -1], encoders.py:756-758,:906)
+    lnf.x = xf + (size_t)L * D; lnf.ldx = S * D; lnf.gamma1 = h->uni_ln_g; lnf.beta = h->uni_ln_b; lnf.y = normalize ? tmpf : text_emb; lnf.ldy = D;
+    lnf.M = Q; lnf.D = D;
+    CK(vp::f32::layernorm(st, lnf)); h->mark(st, "text.unimodal_ln");
+    if (normalize) { CK(vp::launch_l2norm(st, tmpf, text_emb, Q, D)); h->mark(st, "text.l2norm"); }
+    return VP_OK;
+  }
+  if ((rc = ensure_workspace(h, M, D, 4 * D)) != VP_OK) return rc;
   bf16* x = static_cast<bf16*>(h->ws_x.p);
   h->mark(st, nullptr, false);   // trace: start of this forward
   CK(vp::launch_text_embed(st, ids, paddings, h->tok_emb, h->d_pe, h->cls_emb, x, keep, pad_ext, Q, L, D, c.vocabulary_size)); h->mark(st, "text.embed");
@@ -1202,7 +1429,8 @@ int vp_release_workspace(vp_handle* h) {
   if (h == nullptr) return VP_ERR_INVALID;
   DeviceScope device_scope(h->device);
   // cudaFree waits for the device: forwards still in flight finish first.  The buffers grow again on the next call.
-  DevBuf* bufs[] = {&h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats};
+  DevBuf* bufs[] = {&h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats,
+                    &h->c_x, &h->c_n, &h->c_qkv, &h->c_u, &h->c_patch, &h->c_pool};
   for (DevBuf* b : bufs) b->release();
   h->stats_stride = 0;
   return VP_OK;

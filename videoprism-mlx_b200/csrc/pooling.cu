@@ -318,8 +318,11 @@ cudaError_t launch_pool(cudaStream_t s, const bf16* x, int num_seq, int S, int D
                         const float* bv, const bf16* wpost, const float* bpost, const float* ln_g1, const float* ln_b, int normalize,
                         float* scratch, float* out, int64_t* launches) {
   const int HD = H * dh;
-  const int ctx_threads = dh < 128 ? dh : 128;
-  if (H > kMaxHeads || 2 * H > kScoreLd || (D % 8) || (dh % 8) || dh > 1024 || (dh % ctx_threads) || num_seq <= 0 || S <= 0) return cudaErrorInvalidValue;
+  if (H > kMaxHeads || 2 * H > kScoreLd || (D % 8) || (dh % 8) || dh <= 0 || dh > 1024 || num_seq <= 0 || S <= 0) return cudaErrorInvalidValue;
+  // pool_ctx_kernel: a block owns ctx_threads columns of ONE head, so ctx_threads must divide dh: the largest multiple of 8
+  // that does, at most 128 (128 for dh = 256, 64 for 64, 88 for the giant configuration's 4 * 1408 / 16 = 352)
+  int ctx_threads = (dh < 128 ? dh : 128) & ~7;
+  while (ctx_threads > 8 && (dh % ctx_threads)) ctx_threads -= 8;
   if (reinterpret_cast<uintptr_t>(scratch) & 15) return cudaErrorInvalidValue;
   const int nchunk = (S + kChunk - 1) / kChunk;
   const size_t n = static_cast<size_t>(num_seq);

@@ -102,10 +102,16 @@ class _Module:
 
     def __init__(self, **config):
         self.config = dict(config)
-        self.fprop_dtype = None  # accepted for get_model(fprop_dtype=...) compatibility; compute is bf16 / fp32-accumulate
+        # get_model(fprop_dtype=...): None (default) = the production path (bf16 tensor cores, fp32 accumulation, fp32
+        # features out); bfloat16 = the same with bf16 features out; an EXPLICIT float32 selects the fp32 check mode
+        self.fprop_dtype = None
+        # fp32 check mode (vp_create_ex + VP_FLAG_CHECK_FP32): the whole forward in float32 on the CUDA cores, ~50x slower,
+        # held to the reference's own fp32 envelope.  Also switched on for every model by VP_CHECK_FP32=1.
+        self.check_fp32 = os.environ.get("VP_CHECK_FP32", "0") not in ("", "0")
         self._handle: Optional[C.c_void_p] = None
         self._loaded_state_id: Optional[int] = None
         self._loaded_state_ref = None
+        self._loaded_fingerprint = None
 
     # -- handle -------------------------------------------------------------------------------
     def _vp_config(self) -> _lib.VpConfig:
@@ -138,7 +144,10 @@ class _Module:
                     device = int(torch.cuda.current_device())
             except ImportError:
                 pass
-            _lib.check(lib.vp_create_on_device(C.byref(cfg), device, C.byref(h)), None)
+            d = self.fprop_dtype
+            explicit_f32 = d is not None and "float32" in (getattr(d, "__name__", None) or str(d))
+            flags = _lib.VP_FLAG_CHECK_FP32 if (self.check_fp32 or explicit_f32) else 0
+            _lib.check(lib.vp_create_ex(C.byref(cfg), device, flags, C.byref(h)), None)
             self._handle = h
         return self._handle
 
@@ -190,10 +199,26 @@ class _Module:
         _lib.check(lib.vp_finalize(h), h)
         self._loaded_state_id = id(variables)
         self._loaded_state_ref = variables  # keeps id() stable
+        self._loaded_fingerprint = self._fingerprint(variables)
         return self
 
+    @staticmethod
+    def _fingerprint(variables):
+        """Identity of every leaf (key, object id, data pointer, shape): changes when a leaf of the tree is REPLACED, also in a
+        dict that is mutated in place.  Element-wise writes into an uploaded array are not detected (that would mean hashing
+        hundreds of MB per call): call load_state() again after such writes."""
+        flat = _flatten(variables) if any(isinstance(v, Mapping) for v in variables.values()) else variables
+        out = []
+        for k in sorted(flat):
+            v = flat[k]
+            ptr = v.data_ptr() if _is_torch(v) else (v.ctypes.data if isinstance(v, np.ndarray) else 0)
+            out.append((k, id(v), ptr, tuple(getattr(v, "shape", ()))))
+        return tuple(out)
+
     def _bind(self, variables):
-        if variables is not None and id(variables) != self._loaded_state_id:
+        if variables is None:
+            return
+        if id(variables) != self._loaded_state_id or self._fingerprint(variables) != self._loaded_fingerprint:
             self.load_state(variables)
 
     def apply(self, variables, *args, **kwargs):
@@ -492,8 +517,9 @@ def has_model(model_name: str, models: Optional[Mapping[str, Callable]] = None) 
 
 
 def get_model(model_name: Optional[str], model_fn: Optional[Callable] = None, models: Optional[Mapping[str, Callable]] = None,
-              fprop_dtype=None):
-    """models.get_model (models.py:268-303): name (or HF id) -> configured module (no weights yet)."""
+              fprop_dtype=None, check_fp32: Optional[bool] = None):
+    """models.get_model (models.py:268-303): name (or HF id) -> configured module (no weights yet).
+    `check_fp32=True` (extension; also `fprop_dtype=float32` given explicitly, or VP_CHECK_FP32=1) selects the fp32 check mode."""
     if model_fn is None:
         assert model_name is not None
         models = models or MODELS
@@ -508,6 +534,8 @@ def get_model(model_name: Optional[str], model_fn: Optional[Callable] = None, mo
     model = model_fn()
     if fprop_dtype is not None:
         model.fprop_dtype = fprop_dtype
+    if check_fp32 is not None:
+        model.check_fp32 = bool(check_fp32)
     return model
 
 
@@ -663,17 +691,14 @@ def load_classifier(model_name: str, num_classes: int, weights_path: Optional[st
     return model
 
 
-_PINNED_KEEPALIVE = {}
-
-
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     """A numpy array backed by page-locked host memory (cudaHostAlloc through torch): H2D / D2H copies of such
-    buffers are asynchronous DMAs, which is what lets the host entry points overlap copies with compute."""
+    buffers are asynchronous DMAs, which is what lets the host entry points overlap copies with compute.  The array's
+    `.base` chain holds the torch tensor, so the pinned block is freed when the array is garbage collected."""
     import torch
-    t = torch.empty(tuple(shape), dtype={np.float32: torch.float32, np.int32: torch.int32}[np.dtype(dtype).type], pin_memory=True)
-    a = t.numpy()
-    _PINNED_KEEPALIVE[a.ctypes.data] = t
-    return a
+    kinds = {np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8, np.uint16: torch.uint16}
+    t = torch.empty(tuple(shape), dtype=kinds[np.dtype(dtype).type], pin_memory=True)
+    return t.numpy()
 
 
 def compute_similarity_matrix(video_emb, text_emb):
