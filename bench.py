@@ -109,6 +109,48 @@ class ClockSampler:
                 "power_w_max": max(power_load or power), "reasons_window": "first warm-up step .. end of the timed region"}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pins this rank (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA node its
+    GPU hangs off, so that 8 ranks' H2D / D2H streams do not cross the socket interconnect.  Returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def pipelined_e2e(submit, wait, n_steps):
+    """The serving loop of the asynchronous host API: submit step i, then wait for step i-1 (two calls in flight), so the
+    H2D of step i+1 and the D2H of step i-1 overlap the forward of step i.  Every step's copies happen inside the timed
+    region; returns wall-clock seconds for n_steps steps (all results delivered)."""
+    import torch
+    t0 = time.perf_counter()
+    prev = None
+    for i in range(n_steps):
+        tk = submit(i)
+        if prev is not None:
+            wait(prev)
+        prev = tk
+    wait(prev)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
 def cpu_oracle_clips_per_s(model: str, steps: int, warmup: int, budget_s: float):
     """The reference's CPU path: fp32 PyTorch-CPU restatement of the Flax forward (oracle/), 1 clip per step."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -160,20 +202,49 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_oracle_retrieval(model: str, budget_s: float):
+    """CPU baseline of the retrieval workload: the oracle's video-text forward on 1 clip + 4 queries per run."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import videoprism_oracle as O
+    try:
+        n_cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_cores))
+    name = {"base": "videoprism_lvt_public_v1_base", "large": "videoprism_lvt_public_v1_large"}[model]
+    cfg = O.CONFIGS[name]
+    W = O.make_synthetic_weights(cfg)
+    video = O.make_video(1, 16, 288, seed=0)
+    ids, pad = O.make_text(4, vocab=cfg["vocabulary_size"])
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(6):
+        t0 = time.perf_counter()
+        O.run_clip(cfg, W, video, ids, pad)
+        if i >= 1:
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s and times:
+            break
+    mean = sum(times) / len(times)
+    return 1.0 / mean, len(times), torch.get_num_threads(), mean
+
+
 def run_retrieval(args):
     """BASELINE.json configs[3]/[4]: videoprism_lvt_public_v1_{base,large}; clips and text queries sharded over the
-    ranks, pooled embeddings all-gathered (NCCL), similarity matrix [clips, queries] on every rank."""
+    ranks, pooled embeddings all-gathered (NCCL, one collective), similarity matrix [clips, queries] on every rank."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import videoprism_b200 as vp
-    from videoprism_b200.retrieval import retrieval_similarity, shard_range
+    from videoprism_b200.retrieval import gather_embedding_pair, retrieval_similarity, shard_range
     name = {"base": "videoprism_lvt_public_v1_base", "large": "videoprism_lvt_public_v1_large"}[args.model]
     model = vp.get_model(name)
     model.load_state(vp.synthetic_state(model, seed=1234))
@@ -182,12 +253,14 @@ def run_retrieval(args):
     lo, hi = shard_range(n_clips, rank, world)
     qlo, qhi = shard_range(n_q, rank, world)
     rng = np.random.default_rng(100 + rank)
-    video = torch.from_numpy(rng.random((hi - lo, 16, 288, 288, 3), dtype=np.float32)).cuda()
+    host_video = torch.from_numpy(rng.random((hi - lo, 16, 288, 288, 3), dtype=np.float32)).pin_memory()
+    video = host_video.cuda()
     ids_all = np.random.default_rng(2).integers(1, 32000, (n_q, 64), dtype=np.int32)
     lens = np.random.default_rng(3).integers(4, 33, (n_q,))
     pad_all = (np.arange(64)[None, :] >= lens[:, None]).astype(np.float32)
     ids_all = np.where(pad_all > 0, 0, ids_all).astype(np.int32)
-    ids = torch.from_numpy(ids_all[qlo:qhi]).cuda(); pad = torch.from_numpy(pad_all[qlo:qhi]).cuda()
+    host_ids = torch.from_numpy(ids_all[qlo:qhi].copy()).pin_memory(); host_pad = torch.from_numpy(pad_all[qlo:qhi].copy()).pin_memory()
+    ids = host_ids.cuda(); pad = host_pad.cuda()
     warmup = max(args.warmup, 3)
 
     def barrier():
@@ -195,35 +268,118 @@ def run_retrieval(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def step():
+        return retrieval_similarity(model, video, ids, pad, total_clips=n_clips, total_queries=n_q)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.1)
+    t_load0 = time.time()
     for _ in range(warmup):
-        sim = retrieval_similarity(model, video, ids, pad)
+        sim = step()
     barrier()
     l0 = model.kernel_launches
+    t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        sim = retrieval_similarity(model, video, ids, pad)
+        sim = step()
     e1.record()
     barrier()
+    clocks = sampler.stop(t_wall0, time.time(), t_load0) if rank == 0 else None
+    launches = int(model.kernel_launches - l0)
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
+
+    # ---- e2e through the public API with HOST buffers: per step the clips (float32, pinned) go host->device through the
+    # chunk-pipelined asynchronous entry point, ids / paddings are copied host->device, the embeddings are exchanged and the
+    # similarity matrix is read back to the host.
+    e2e = None
+    if not args.no_e2e:
+        hv = host_video.numpy()
+        v_out = [vp.pinned_empty((hi - lo, model.config["model_dim"])) for _ in range(2)]
+
+        def e2e_step(i):
+            tk, v_host = model.embed_video_async(hv, out=v_out[i & 1])
+            ids_d = host_ids.cuda(non_blocking=True); pad_d = host_pad.cuda(non_blocking=True)
+            _, t_d, _ = model(None, ids_d, pad_d)
+            model.wait(tk)
+            v_d = torch.from_numpy(v_host).cuda(non_blocking=True)
+            v_all, t_all = gather_embedding_pair(v_d, t_d, n_clips, n_q)
+            return vp.compute_similarity_matrix(v_all, t_all).cpu()
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            sim_host = e2e_step(i)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        clip_bytes = 16 * 288 * 288 * 3 * 4
+        e2e = {"value": n_clips * n_e2e / float(tt.item()), "unit": "clips/s",
+               "h2d_bytes_per_step": (hi - lo) * clip_bytes + (qhi - qlo) * 64 * 8 + (hi - lo) * model.config["model_dim"] * 4,
+               "d2h_bytes_per_step": (hi - lo) * model.config["model_dim"] * 4 + n_clips * n_q * 4, "steps": n_e2e,
+               "queries_per_s": n_q * n_e2e / float(tt.item()),
+               "how": "FactorizedVideoCLIP.embed_video_async(numpy pinned clips) -> vp_clip_video_forward_host_async (chunk-pipelined H2D + "
+                      "forward), ids / paddings host->device, text forward, wait, all-gather (one collective), similarity matrix read back "
+                      "to the host; wall clock, max over ranks"}
+
+    peaks, src = measured_peaks()
+    roof, cpu = None, None
     if rank == 0:
+        D, F, Hh = model.config["model_dim"], model.config["mlp_dim"], model.config["num_heads"]
+        model.trace(True)
+        for _ in range(2):
+            step()
+        rows = model.trace_report()
+        model.trace(False)
+        total_ms = [r for r in rows if r[0] == "TOTAL"][0][2]
+        shares = {r[0]: round(r[2] / total_ms, 4) for r in rows if r[0] != "TOTAL"}
+        M = (hi - lo) * 16 * 256
+        ffn1 = [r for r in rows if r[0] in ("spatial.ffn1", "temporal.ffn1", "aux.ffn1")]
+        k_ms = sum(r[2] for r in ffn1) / sum(r[1] for r in ffn1)
+        flops = 2.0 * M * F * D
+        ach = flops / (k_ms * 1e-3) / 1e12
+        aux = [r for r in rows if r[0] == "aux.attn"]
+        aux_ms = sum(r[2] for r in aux) / max(1, sum(r[1] for r in aux))
+        aux_flops = 4.0 * 4096 * 4096 * 64 * Hh * (hi - lo)
+        aux_tf = aux_flops / (aux_ms * 1e-3) / 1e12 if aux_ms > 0 else None
+        peak = float(peaks["bf16_tflops_sustained"]); burst = float(peaks.get("bf16_tflops", peak))
         gf = {"base": 1231.04 - 38.71 + 0.15, "large": 3410.92 - 68.80 + 0.27}[args.model]   # pooler in its executed (collapsed) form
         gfq = {"base": 11.20, "large": 19.84}[args.model]
         tf = (n_clips * gf + n_q * gfq) / ms / world   # GF/ms = TF/s per GPU
-        peaks, src = measured_peaks()
+        roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel<256,GELU> FFN1 (LayerNorm folded) [{M}x{D}]x[{D}x{F}]", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "frac_of_burst_peak": ach / burst, "traffic": None, "peak_source": src + ", bf16_tflops_sustained",
+                "ms_per_launch": k_ms, "flops_per_launch": flops, "share_of_step": round(sum(r[2] for r in ffn1) / total_ms, 4),
+                "how": "CUDA events after every launch on the launch stream (vp_trace), 2 extra steps of the same workload",
+                "kernel_shares": shares,
+                "attention_aux": {"kernel": "attn_kloop_tcgen05_kernel (auxiliary encoder, S = 4096, dh = 64)", "ms_per_launch": aux_ms,
+                                  "flops_per_launch": aux_flops, "achieved": aux_tf, "frac": (aux_tf / peak) if aux_tf else None,
+                                  "frac_of_burst_peak": (aux_tf / burst) if aux_tf else None},
+                "step": {"achieved": tf, "frac": tf / peak,
+                         "note": "whole step per GPU; algorithmic GF with the pooling head in its executed single-query form"}}
+        if world == 1 and not args.no_cpu_baseline:
+            v, n_runs, threads, mean = cpu_oracle_retrieval(args.model, budget_s=25.0)
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                   "sample": f"1 clip + 4 text queries per run, 1 warm-up + {n_runs} timed runs (<= 25 s of CPU work), mean {mean:.2f} s; fp32 "
+                             "PyTorch-CPU restatement of FactorizedVideoCLIP (oracle/), all host threads torch uses"}
         print(json.dumps({
             "metric": "clips/sec (video-text retrieval step)", "value": n_clips / (ms / 1e3), "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{name}: {n_clips} clips x {n_q} text queries, all-gather of pooled embeddings, similarity matrix",
-                       "clips_per_gpu": hi - lo, "queries_per_gpu": qhi - qlo, "parallelism": f"dp{world} + all-gather (NCCL)"},
-            "queries_per_s": n_q / (ms / 1e3), "similarity_shape": list(sim.shape), "gpu_launches": int(model.kernel_launches - l0),
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["bf16_tflops_sustained"], "peak_source": src, "traffic": None,
-                         "note": "whole step per GPU; algorithmic GF with the pooling head in its executed single-query form"}}), flush=True)
+                       "clips_per_gpu": hi - lo, "queries_per_gpu": qhi - qlo, "parallelism": f"dp{world} + all-gather (NCCL, one collective per step)",
+                       "l2": f"inputs larger than L2: {(hi - lo) * 16 * 288 * 288 * 3 * 4 / 2**20:.0f} MiB of clips per step", "numa_node_rank0": numa_node},
+            "queries_per_s": n_q / (ms / 1e3), "similarity_shape": list(sim.shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -262,6 +418,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local)   # before any pinned allocation
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout: stdout carries ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -328,37 +485,45 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_np = host_in.numpy()
-        out_bytes = b_local * T * 256 * model.config["model_dim"] * 4
-        host_out = vp.pinned_empty((b_local, T * 256, model.config["model_dim"]))
-        for i in range(2):
-            model(host_np, out=host_out)
-        barrier()
+        dm = model.config["model_dim"]
+        out_bytes = b_local * T * 256 * dm * 4
+        host_out = [vp.pinned_empty((b_local, T * 256, dm)) for _ in range(2)]
         n_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            model(host_np, out=host_out)   # pinned in / pinned out; the call returns after the last D2H chunk has landed
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": args.global_batch * n_e2e / float(tt.item()), "unit": "clips/s", "h2d_bytes_per_step": b_local * clip_bytes,
-               "d2h_bytes_per_step": out_bytes, "steps": n_e2e,
-               "how": "models.FactorizedEncoder.__call__(numpy, out=pinned) -> vp_encoder_forward_host: per step H2D of the clips, forward, D2H of the features (chunk-pipelined over 3 streams), wall clock, max over ranks"}
 
-        # same call fed with uint8 frames (as decoded; the /255 of video_utils.load_video runs on the device): 4x smaller H2D
-        u8 = torch.randint(0, 256, (b_local, T, S, S, 3), dtype=torch.uint8).pin_memory().numpy()
-        model(u8, out=host_out)
+        def timed(submit, n=n_e2e):
+            pipelined_e2e(submit, model.wait, 2)   # warm-up of this variant (workspace, staging buffers)
+            barrier()
+            tt = torch.tensor([pipelined_e2e(submit, model.wait, n)], device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return args.global_batch * n / float(tt.item())
+
+        # headline: float32 clips in, float32 features out, pinned host buffers, two calls in flight
+        v_async = timed(lambda i: model.forward_async(host_np, out=host_out[i & 1])[0])
+        e2e = {"value": v_async, "unit": "clips/s", "h2d_bytes_per_step": b_local * clip_bytes, "d2h_bytes_per_step": out_bytes, "steps": n_e2e,
+               "how": "models.FactorizedEncoder.forward_async(numpy, out=pinned) + wait -> vp_encoder_forward_host_async / vp_wait: every step "
+                      "copies its clips host->device and its features device->host (chunk-pipelined over 3 streams); two steps are in flight, "
+                      "so a step's copies overlap its neighbours' forwards; wall clock over all steps until the last result has landed, max over ranks"}
+        # the same with one blocking call per step (nothing overlaps across steps): models.FactorizedEncoder.__call__(numpy)
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            model(u8, out=host_out)
+            model(host_np, out=host_out[0])
         torch.cuda.synchronize()
         tt = torch.tensor([time.perf_counter() - t0], device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e["uint8_frames"] = {"value": args.global_batch * n_e2e / float(tt.item()), "unit": "clips/s",
+        e2e["blocking_call"] = {"value": args.global_batch * n_e2e / float(tt.item()), "unit": "clips/s",
+                                "h2d_bytes_per_step": b_local * clip_bytes, "d2h_bytes_per_step": out_bytes}
+        # uint8 frames in (as decoded; the /255 of video_utils.load_video runs on the device): 4x smaller H2D
+        u8 = torch.randint(0, 256, (b_local, T, S, S, 3), dtype=torch.uint8).pin_memory().numpy()
+        e2e["uint8_frames"] = {"value": timed(lambda i: model.forward_async(u8, out=host_out[i & 1])[0]), "unit": "clips/s",
                                "h2d_bytes_per_step": b_local * clip_bytes // 4, "d2h_bytes_per_step": out_bytes}
+        # uint8 frames in, bfloat16 features out: half the D2H as well
+        out16 = [vp.pinned_empty((b_local, T * 256, dm), dtype=np.uint16) for _ in range(2)]
+        e2e["uint8_frames_bf16_features"] = {
+            "value": timed(lambda i: model.forward_async(u8, out=out16[i & 1], bf16_features=True)[0]), "unit": "clips/s",
+            "h2d_bytes_per_step": b_local * clip_bytes // 4, "d2h_bytes_per_step": out_bytes // 2}
 
     # ---- roofline of the dominant kernel (FFN1 GEMM: folded LayerNorm + GELU epilogue), timed IN SITU: the engine
     # records a CUDA event after every launch on the launch stream (vp_trace), a few more steps of the same workload
@@ -388,8 +553,22 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(f"ffn1_ln_gelu_{M}x{F}x{D}")
+        burst = float(peaks.get("bf16_tflops", peak))
+        sm_mhz = (clocks or {}).get("sm_mhz")
+        attn = [r for r in rows if r[0] == "spatial.attn"]
+        attn_ms = sum(r[2] for r in attn) / max(1, sum(r[1] for r in attn))
+        attn_flops = 4.0 * 256 * 256 * 64 * model.config["num_heads"] * (b_local * T)
+        attn_tf = attn_flops / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else None
         roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel<256,GELU> FFN1 (LayerNorm folded) [{M}x{D}]x[{D}x{F}]", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src + ", bf16_tflops_sustained",
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": "static: the committed `ncu --set full` capture of this launch shape (profiles/ncu_traffic.json), not measured in this run",
+                "frac_of_burst_peak": ach / burst,
+                "peak_note": ("sampled SM clock above 1.5 GHz: the kernel is not power-capped at this duty, compare with the burst peak "
+                              f"({burst:.0f} TF)" if (sm_mhz or 0) > 1500 else "SM clock power-capped: the sustained peak is the denominator"),
+                "attention": {"kernel": "attn_kloop_tcgen05_kernel (spatial, S = 256, dh = 64)", "ms_per_launch": attn_ms, "flops_per_launch": attn_flops,
+                              "achieved": attn_tf, "frac": (attn_tf / peak) if attn_tf else None, "frac_of_burst_peak": (attn_tf / burst) if attn_tf else None,
+                              "note": "4*S^2*dh flop per head-sequence; exponentials and the cap are not counted"},
+                "peak_source": peak_src + ", bf16_tflops_sustained",
                 "ms_per_launch": k_ms, "flops_per_launch": flops, "launches_timed": sum(r[1] for r in ffn1),
                 "share_of_step": round(sum(r[2] for r in ffn1) / total_ms, 4),
                 "how": "CUDA events after every launch on the launch stream (vp_trace), averaged over the kernel's launches in "
@@ -412,7 +591,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{name} encoder forward, 16x288x288x3 clips, random-init weights", "global_batch": args.global_batch,
                        "clips_per_gpu": b_local, "parallelism": f"dp{world} (batch shard, no collective)",
-                       "l2": f"inputs larger than L2: {n_bufs} rotating device input buffers of {b_local * clip_bytes / 2**20:.0f} MiB"},
+                       "l2": f"inputs larger than L2: {n_bufs} rotating device input buffers of {b_local * clip_bytes / 2**20:.0f} MiB",
+                       "numa_node_rank0": numa_node},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -7,8 +7,11 @@
  * Conventions: every function returns 0 on success and a negative vp_status on failure (message via
  * vp_last_error); no exception crosses the ABI; the caller owns all I/O buffers and the stream; the
  * handle owns the repacked weights and its workspace; all device work is enqueued on the given
- * stream with no internal host synchronisation (the *_host variants synchronise the stream once,
- * after the device->host copy).  A handle is bound to one CUDA device (the current one at vp_create,
+ * stream.  In steady state (same shapes as an earlier call) the device-buffer entry points and the
+ * *_host_async ones do not synchronise with the host; the FIRST call with a new shape may: the
+ * workspace grows with cudaMalloc / cudaFree and resized position tables are uploaded with a stream
+ * synchronisation (so capture CUDA graphs only after one warm-up call per shape).  The synchronous
+ * *_host variants wait once, for the device->host copy.  A handle is bound to one CUDA device (the current one at vp_create,
  * or the one named in vp_create_on_device); every entry point selects that device for the duration of
  * the call and restores the caller's current device before returning.  A handle is not thread-safe,
  * and because all forwards of a handle share its workspace, consecutive calls on one handle must be
@@ -116,6 +119,18 @@ VP_API int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, in
 VP_API int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
                             float* out_features, float* spatial_features, void* stream);
 
+/* Asynchronous host-buffer call: enqueues the chunk-pipelined H2D copies / forward / D2H copies and RETURNS; *ticket names
+ * the call for vp_wait, which blocks until its results are in out_features (and spatial_features).  Consecutive calls
+ * pipeline on the device: the H2D of call k+1 overlaps the forward of call k, the D2H of call k the forward of call k+1
+ * (this is how a serving loop hides PCIe entirely).  video: in_dtype VP_F32 or VP_U8; out_features: out_dtype VP_F32 or
+ * VP_BF16 (half the D2H bytes; spatial_features is fp32 and requires VP_F32).  The host buffers must stay valid (and
+ * should be page-locked) until vp_wait returns.  At most 8 calls may be outstanding.  Replaces the same reference call as
+ * vp_encoder_forward (`model.apply(state, video, ...)`; JAX dispatch is asynchronous too, block_until_ready = vp_wait). */
+VP_API int vp_encoder_forward_host_async(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W,
+                                  const float* frame_paddings, void* out_features, float* spatial_features, int out_dtype,
+                                  void* stream, uint64_t* ticket);
+VP_API int vp_wait(vp_handle* h, uint64_t ticket);
+
 /* Same two calls for uint8 frames [B,T,H,W,3] (0..255) as cv2 decodes them: the `astype(float32) / 255.0` of
  * video_utils.load_video (videoprism/video_utils.py:88-93) happens on the device inside the patchify kernel,
  * bit-identically, so the host-to-device copy is 4x smaller. */
@@ -135,8 +150,15 @@ VP_API int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T,
  *    ids [Q,L] int32, paddings [Q,L] fp32 (1 = pad), device memory; text_emb [Q,D] fp32. */
 VP_API int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
                          float* text_emb, void* stream);
+VP_API int vp_clip_video_forward_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
+                             int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                             float* frame_embeddings, void* stream);   /* uint8 frames, / 255 on the device */
 VP_API int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, int normalize,
                                float* video_emb, void* stream);
+/* chunk-pipelined, asynchronous host-buffer form (see vp_encoder_forward_host_async): fp32 or uint8 frames, optional
+ * frame_paddings [B,T] (host), pooled video embeddings [B,D] fp32 to host memory; vp_wait(ticket) for the result */
+VP_API int vp_clip_video_forward_host_async(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W,
+                                     const float* frame_paddings, int normalize, float* video_emb, void* stream, uint64_t* ticket);
 VP_API int vp_clip_text_forward_host(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,
                               float* text_emb, void* stream);
 

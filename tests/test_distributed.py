@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from videoprism_b200.retrieval import gather_embeddings, shard_range
+from videoprism_b200.retrieval import gather_embedding_pair, gather_embeddings, shard_range
 
 
 def test_shard_range_is_a_contiguous_partition():
@@ -41,6 +41,16 @@ def _worker(rank, world, port, n_video, n_text, dim, out_dir):
         lo, hi = shard_range(n_text, rank, world)
         t_all = gather_embeddings(full_t[lo:hi].clone(), total=n_text)
         ok = torch.equal(v_all, full_v) and torch.equal(t_all, full_t)
+        # the same gather without the global count (sizes exchanged first) and as ONE collective for both matrices
+        lo_v, hi_v = shard_range(n_video, rank, world)
+        ok = ok and torch.equal(gather_embeddings(full_v[lo_v:hi_v].clone()), full_v)
+        v2, t2 = gather_embedding_pair(full_v[lo_v:hi_v].clone(), full_t[lo:hi].clone(), n_video, n_text)
+        ok = ok and torch.equal(v2, full_v) and torch.equal(t2, full_t)
+        try:   # a shard that does not follow shard_range is refused, not silently misplaced
+            gather_embeddings(full_v[: hi_v - lo_v + 1].clone(), total=n_video)
+            ok = False
+        except RuntimeError:
+            pass
         sim = v_all @ t_all.T
         np.save(os.path.join(out_dir, f"sim_{rank}.npy"), sim.numpy())
         with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:

@@ -110,6 +110,58 @@ def test_base_encoder_parity_config1():
     assert m.kernel_launches > 0
 
 
+def _stress_weights(kind):
+    cfg = O.CONFIGS["videoprism_public_v1_base"]
+    base = O.make_synthetic_weights(cfg)
+    W = dict(base)
+    if kind == "proj_x3":          # all projection matrices x3 (N(0, 0.06))
+        W = {k: (v * 3 if v.ndim >= 2 and "emb_var" not in k else v) for k, v in base.items()}
+    elif kind == "qk_x8":          # query / key projections x8: logits reach the 50 tanh cap, softmax rows are peaked
+        for k in W:
+            if k.endswith("self_attention/query/w") or k.endswith("self_attention/key/w"):
+                W[k] = W[k] * 8
+    elif kind == "massive":        # two massive residual channels (+60 / -45 on every token), as released ViTs have
+        b = W["params/patch_projection/linear/bias"].copy()
+        b[[7, 300]] = [60.0, -45.0]
+        W["params/patch_projection/linear/bias"] = b
+    elif kind == "ln":             # LayerNorm scale x3, bias +0.5: stresses the LayerNorm folded into the GEMMs
+        for k in W:
+            if k.endswith("layer_norm/bias"):
+                W[k] = W[k] + 0.5
+            if k.endswith("layer_norm/scale"):
+                W[k] = W[k] * 3
+    return cfg, W
+
+
+@pytest.mark.parametrize("kind,cos_min", [("proj_x3", 0.999), ("massive", 0.999), ("ln", 0.999), ("qk_x8", 0.998)])
+def test_base_encoder_parity_under_harsher_weight_statistics(kind, cos_min):
+    """Parity beyond the near-uniform attention of the N(0, 0.02) random init (weights of released checkpoints have logits
+    that reach the cap and a few massive residual channels).  Three of the four cases hold the 0.999 bound.
+
+    SECOND, JUSTIFIED BOUND for `qk_x8` (|logit| ~ 30..50, single keys carry a row): 0.998.  There the loss is not in the
+    softmax kernel (test_attention_peaked_logits holds it to its derived bound up to the saturated cap) but in the bf16
+    rounding of q and k THEMSELVES, the operands of the tensor-core q.k^T: a relative operand error of 2^-9 on a logit of 30
+    is 0.06..0.1 in the exponent, i.e. several per cent in individual softmax weights.  Evidence, all in this test:
+      * the fp32 check mode of this library (same kernels' algorithm, fp32 operands) agrees with the oracle to < 1e-3 max-abs
+        on the same weights, so the algorithm (cap, softmax, folded LayerNorm) is right under peaked logits;
+      * the reference's own algorithm evaluated with every tensor in bfloat16 (its fprop_dtype=bfloat16 mode, run through
+        the oracle on the CPU: profiles/r1_stress_parity.txt) gets min cosine 0.99480 on this case: the production path
+        (bf16 operands, fp32 accumulation / softmax / residual adds) loses 4x less than that."""
+    import videoprism_b200 as vp
+    name = "videoprism_public_v1_base"
+    cfg, W = _stress_weights(kind)
+    v = O.make_video(1, 16, 288, seed=3)
+    want, _ = O.run_encoder(cfg, W, v)
+    got, _ = vp.get_model(name).apply(W, v, train=False)
+    c, e = report(f"base encoder, harsher weights [{kind}] (bf16 path)", got, want)
+    assert c >= cos_min
+    if kind == "qk_x8":
+        chk, _ = vp.get_model(name, check_fp32=True).apply(W, v, train=False)
+        c32, e32 = report(f"base encoder, harsher weights [{kind}] (fp32 check mode)", chk, want)
+        assert c32 >= 0.99999 and e32 < 1e-3
+        assert c > 0.9948      # better than the all-bf16 evaluation of the reference algorithm on the same case
+
+
 def test_large_encoder_parity_config3_shapes():
     """BASELINE.json configs[2]: videoprism_public_v1_large (24+4 blocks, D=1024, H=16, F=4096); its temporal
     table has 8 rows and is bilinearly resized to the 16 frames (encoders.py:551-552)."""

@@ -44,6 +44,10 @@ _PROTOS = {
     "vp_encoder_forward_host": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "vp_encoder_forward_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "vp_encoder_forward_host_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "vp_encoder_forward_host_async": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, C.POINTER(C.c_uint64)]),
+    "vp_wait": (_I, [_P, C.c_uint64]),
+    "vp_clip_video_forward_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "vp_clip_video_forward_host_async": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, C.POINTER(C.c_uint64)]),
     "vp_clip_video_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "vp_clip_text_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "vp_clip_video_forward_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),

@@ -141,7 +141,12 @@ struct vp_handle {
   // host-buffer pipeline (vp_encoder_forward_host)
   bool pipe_init = false;
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  bool comp_rec[2] = {false, false}, out_rec[2] = {false, false};   // ev_comp / ev_out of the slot have been recorded at least once
+  uint64_t chunk_seq = 0;     // chunks enqueued so far, over ALL host calls: slot = chunk_seq & 1, so consecutive calls pipeline
+  static constexpr int kTickets = 8;
+  cudaEvent_t ev_done[kTickets] = {};   // ev_done[t % kTickets]: results of the call with ticket t are in the caller's buffers
+  uint64_t next_ticket = 1;
   int host_chunk_clips = 0;   // 0 = automatic
   size_t stats_stride = 0;    // floats between the two LayerNorm-statistics buffers
 
@@ -1000,9 +1005,10 @@ void vp_destroy(vp_handle* h) {
   if (h->d_temporal_pos) cudaFree(h->d_temporal_pos);
   if (h->d_pe) cudaFree(h->d_pe);
   if (h->pipe_init) {
+    cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_out);
     cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_comp[i]); cudaEventDestroy(h->ev_out[i]); }
-    cudaEventDestroy(h->ev_start);
+    for (int i = 0; i < vp_handle::kTickets; ++i) cudaEventDestroy(h->ev_done[i]);
   }
   DevBuf* bufs[] = {&h->staging, &h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats,
                     &h->c_x, &h->c_n, &h->c_qkv, &h->c_u, &h->c_patch, &h->c_pool};
@@ -1117,36 +1123,31 @@ int vp_encoder_forward_u8(vp_handle* h, const uint8_t* video, int B, int T, int 
   return encoder_forward_dev(h, video, VP_U8, B, T, H, W, frame_paddings, out_features, spatial_features, out_dtype, stream);
 }
 
-// Host-buffer entry point, software-pipelined over clip chunks: H2D of chunk i+1 (copy-in stream), forward of
-// chunk i (caller's stream) and D2H of chunk i-1 (copy-out stream) overlap; device staging is double buffered
-// and ordered with events.  Pinned host buffers give true DMA overlap; pageable ones still work (staged copies).
-static int encoder_forward_host_impl(vp_handle* h, const void* video_v, int in_dtype, int B, int T, int H, int W,
-                                     const float* frame_paddings, float* out_features, float* spatial_features, void* stream) {
-  const char* video = static_cast<const char*>(video_v);
-  const size_t esz = in_dtype == VP_U8 ? 1 : sizeof(float);
-  DeviceScope device_scope(h ? h->device : -1);
-  int rc = check_ready(h);
-  if (rc != VP_OK) return rc;
-  if (video == nullptr || out_features == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
-  if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || H % h->cfg.patch_size || W % h->cfg.patch_size) return h->fail(VP_ERR_INVALID, "bad clip shape");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!h->pipe_init) {
-    CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
-    }
-    CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-    h->pipe_init = true;
+// ---------------------------------------------------------------------------------------------- host-buffer pipeline
+// Host-buffer entry points are software-pipelined over clip chunks: H2D of chunk i+1 (copy-in stream), forward of chunk i
+// (caller's stream) and D2H of chunk i-1 (copy-out stream) overlap; device staging is double buffered and ordered with
+// events.  The slot sequence runs over ALL calls of the handle, and the *_async entry points return once everything is
+// enqueued, so the H2D of call k+1 also overlaps the forward of call k and the D2H of call k overlaps the forward of
+// call k+1 (vp_wait(ticket) blocks until a call's results are in the caller's buffers).  Pinned host buffers give true
+// DMA overlap; pageable ones still work (the runtime stages them and the enqueue blocks).
+static int pipe_setup(vp_handle* h) {
+  if (h->pipe_init) return VP_OK;
+  CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
   }
-  const size_t clip_in = (size_t)T * H * W * 3;
-  const size_t N = (size_t)(H / h->cfg.patch_size) * (W / h->cfg.patch_size);
-  const size_t clip_out = (size_t)T * N * h->cfg.model_dim;
-  // Chunk schedule.  Only the first chunk's H2D and the last chunk's D2H are exposed (everything else overlaps the
-  // forward of a neighbouring chunk), so both ends are small (2 clips); every chunk costs ~0.4 ms of fixed per-launch
-  // overhead (84 launches), so the middle runs 8-clip chunks with 6-clip ramps: 32 clips -> 2 6 8 8 6 2.
+  for (int i = 0; i < vp_handle::kTickets; ++i) CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  h->pipe_init = true;
+  return VP_OK;
+}
+
+// Chunk schedule.  Within one call only the first chunk's H2D and the last chunk's D2H are exposed (everything else
+// overlaps the forward of a neighbouring chunk), so both ends are small (2 clips); every chunk costs ~0.4 ms of fixed
+// per-launch overhead (84 launches), so the middle runs 8-clip chunks with 6-clip ramps: 32 clips -> 2 6 8 8 6 2.
+static std::vector<int> chunk_schedule(const vp_handle* h, int B) {
   std::vector<int> sizes;
   if (h->host_chunk_clips > 0) {
     for (int c0 = 0; c0 < B; c0 += h->host_chunk_clips) sizes.push_back(B - c0 < h->host_chunk_clips ? B - c0 : h->host_chunk_clips);
@@ -1166,59 +1167,144 @@ static int encoder_forward_host_impl(vp_handle* h, const void* video_v, int in_d
     }
     sizes.push_back(2);
   }
+  return sizes;
+}
+
+static int clip_video_forward_dev(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                                  int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                                  float* frame_embeddings, cudaStream_t st);
+
+// mode 0: encoder features (out_dtype VP_F32 / VP_BF16, optional fp32 spatial_features); mode 1: video-text model, pooled
+// video embeddings [B, D] fp32 (`normalize`).  Enqueues everything and records the call's completion event; no host wait.
+static int host_pipeline(vp_handle* h, int mode, const void* video_v, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                         void* out_v, float* spatial_features, int out_dtype, int normalize, cudaStream_t st, uint64_t* ticket) {
+  const char* video = static_cast<const char*>(video_v);
+  const size_t esz = in_dtype == VP_U8 ? 1 : sizeof(float);
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  if (mode == 1 && h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
+  if (video == nullptr || out_v == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
+  if (in_dtype != VP_F32 && in_dtype != VP_U8) return h->fail(VP_ERR_INVALID, "in_dtype must be VP_F32 or VP_U8");
+  if (out_dtype != VP_F32 && out_dtype != VP_BF16) return h->fail(VP_ERR_INVALID, "out_dtype must be VP_F32 or VP_BF16");
+  if (spatial_features != nullptr && out_dtype != VP_F32) return h->fail(VP_ERR_UNSUPPORTED, "spatial_features requires VP_F32 outputs");
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || H % h->cfg.patch_size || W % h->cfg.patch_size) return h->fail(VP_ERR_INVALID, "bad clip shape");
+  if ((rc = pipe_setup(h)) != VP_OK) return rc;
+  const size_t clip_in = (size_t)T * H * W * 3;
+  const size_t N = (size_t)(H / h->cfg.patch_size) * (W / h->cfg.patch_size);
+  const size_t D = h->cfg.model_dim;
+  const size_t clip_out = (size_t)T * N * D;
+  const size_t osz = out_dtype == VP_BF16 ? sizeof(bf16) : sizeof(float);
+  const std::vector<int> sizes = chunk_schedule(h, B);
   const int nchunks = (int)sizes.size();
   int chunk = 0;
   for (int c : sizes) chunk = c > chunk ? c : chunk;
   const size_t in_stride = ((size_t)chunk * clip_in * esz + 255) / 256 * 256;
-  const size_t out_stride = ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256;
-  const size_t pad_bytes = frame_paddings ? (size_t)B * T * sizeof(float) : 0;
+  const size_t out_stride = mode == 0 ? ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256 : 0;
+  const size_t pad_bytes = frame_paddings ? ((size_t)B * T * sizeof(float) + 255) / 256 * 256 : 0;
   CK(h->ws_io_in.ensure(2 * in_stride + 256 + pad_bytes));
-  CK(h->ws_io_out.ensure(2 * out_stride * (spatial_features ? 2 : 1)));
+  CK(h->ws_io_out.ensure(mode == 0 ? 2 * out_stride * (spatial_features ? 2 : 1) : (size_t)B * D * sizeof(float)));
   char* in_base = static_cast<char*>(h->ws_io_in.p);
   char* out_base = static_cast<char*>(h->ws_io_out.p);
   float* d_pad = nullptr;
-  if (frame_paddings) {
+  if (frame_paddings) {   // on the compute stream: ordered after the previous call's kernels that read this region
     d_pad = reinterpret_cast<float*>(in_base + 2 * in_stride);
-    CK(cudaMemcpyAsync(d_pad, frame_paddings, pad_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pad, frame_paddings, (size_t)B * T * sizeof(float), cudaMemcpyHostToDevice, st));
   }
-  // the side streams start after whatever the caller already queued on `st`
-  CK(cudaEventRecord(h->ev_start, st));
-  CK(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
-  CK(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
   int c0 = 0;
   for (int i = 0; i < nchunks; c0 += sizes[i], ++i) {
-    const int b = i & 1;
+    const int b = (int)(h->chunk_seq & 1);
     const int bc = sizes[i];
-    float* d_in = reinterpret_cast<float*>(in_base + b * in_stride);
-    float* d_out = reinterpret_cast<float*>(out_base + b * out_stride);
+    void* d_in = in_base + b * in_stride;
+    char* d_out = out_base + b * out_stride;
     float* d_sp = spatial_features ? reinterpret_cast<float*>(out_base + (2 + b) * out_stride) : nullptr;
-    if (i >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));       // chunk i-2 no longer reads this input buffer
+    if (h->comp_rec[b]) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));   // the forward two chunks ago no longer reads this input slot
     CK(cudaMemcpyAsync(d_in, video + (size_t)c0 * clip_in * esz, (size_t)bc * clip_in * esz, cudaMemcpyHostToDevice, h->s_in));
     CK(cudaEventRecord(h->ev_in[b], h->s_in));
     CK(cudaStreamWaitEvent(st, h->ev_in[b], 0));
-    if (i >= 2) CK(cudaStreamWaitEvent(st, h->ev_out[b], 0));             // chunk i-2's D2H has drained this output buffer
-    rc = encoder_body(h, d_in, in_dtype, bc, T, H, W, d_pad ? d_pad + (size_t)c0 * T : nullptr, d_out, nullptr, false, d_sp, st, nullptr);
+    if (mode == 0 && h->out_rec[b]) CK(cudaStreamWaitEvent(st, h->ev_out[b], 0));   // the D2H two chunks ago has drained this output slot
+    const float* padc = d_pad ? d_pad + (size_t)c0 * T : nullptr;
+    if (mode == 0) {
+      rc = encoder_body(h, d_in, in_dtype, bc, T, H, W, padc, out_dtype == VP_F32 ? reinterpret_cast<float*>(d_out) : nullptr,
+                        out_dtype == VP_BF16 ? reinterpret_cast<bf16*>(d_out) : nullptr, false, d_sp, st, nullptr);
+    } else {
+      rc = clip_video_forward_dev(h, d_in, in_dtype, bc, T, H, W, padc, normalize, reinterpret_cast<float*>(out_base) + (size_t)c0 * D,
+                                  nullptr, nullptr, nullptr, st);
+    }
     if (rc != VP_OK) { cudaDeviceSynchronize(); return rc; }
     CK(cudaEventRecord(h->ev_comp[b], st));
-    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
-    CK(cudaMemcpyAsync(out_features + (size_t)c0 * clip_out, d_out, (size_t)bc * clip_out * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-    if (spatial_features)
-      CK(cudaMemcpyAsync(spatial_features + (size_t)c0 * clip_out, d_sp, (size_t)bc * clip_out * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-    CK(cudaEventRecord(h->ev_out[b], h->s_out));
+    h->comp_rec[b] = true;
+    if (mode == 0) {
+      CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+      CK(cudaMemcpyAsync(static_cast<char*>(out_v) + (size_t)c0 * clip_out * osz, d_out, (size_t)bc * clip_out * osz, cudaMemcpyDeviceToHost, h->s_out));
+      if (spatial_features)
+        CK(cudaMemcpyAsync(spatial_features + (size_t)c0 * clip_out, d_sp, (size_t)bc * clip_out * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+      CK(cudaEventRecord(h->ev_out[b], h->s_out));
+      h->out_rec[b] = true;
+    }
+    h->chunk_seq++;
   }
-  CK(cudaStreamSynchronize(h->s_out));
-  CK(cudaStreamSynchronize(st));
+  if (mode == 1) {   // the pooled embeddings of the whole call, once (B x D floats)
+    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[(h->chunk_seq - 1) & 1], 0));
+    CK(cudaMemcpyAsync(out_v, out_base, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    // the next call's first forward must not overwrite the embedding buffer before this copy has read it
+    CK(cudaEventRecord(h->ev_out[0], h->s_out));
+    CK(cudaStreamWaitEvent(st, h->ev_out[0], 0));
+  }
+  const uint64_t tk = h->next_ticket++;
+  CK(cudaEventRecord(h->ev_done[tk % vp_handle::kTickets], h->s_out));
+  if (ticket) *ticket = tk;
+  return VP_OK;
+}
+
+int vp_wait(vp_handle* h, uint64_t ticket) {
+  if (h == nullptr) return VP_ERR_INVALID;
+  DeviceScope device_scope(h->device);
+  if (!h->pipe_init || ticket == 0 || ticket >= h->next_ticket) return h->fail(VP_ERR_INVALID, "unknown ticket");
+  if (h->next_ticket - ticket > (uint64_t)vp_handle::kTickets) {   // its event slot has been reused: everything that old is long done
+    CK(cudaStreamSynchronize(h->s_out));
+    return VP_OK;
+  }
+  CK(cudaEventSynchronize(h->ev_done[ticket % vp_handle::kTickets]));
+  return VP_OK;
+}
+
+int vp_encoder_forward_host_async(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                                  void* out_features, float* spatial_features, int out_dtype, void* stream, uint64_t* ticket) {
+  DeviceScope device_scope(h ? h->device : -1);
+  if (h == nullptr) return VP_ERR_INVALID;
+  return host_pipeline(h, 0, video, in_dtype, B, T, H, W, frame_paddings, out_features, spatial_features, out_dtype, 0,
+                       static_cast<cudaStream_t>(stream), ticket);
+}
+
+int vp_clip_video_forward_host_async(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                                     int normalize, float* video_emb, void* stream, uint64_t* ticket) {
+  DeviceScope device_scope(h ? h->device : -1);
+  if (h == nullptr) return VP_ERR_INVALID;
+  return host_pipeline(h, 1, video, in_dtype, B, T, H, W, frame_paddings, video_emb, nullptr, VP_F32, normalize,
+                       static_cast<cudaStream_t>(stream), ticket);
+}
+
+static int host_sync_call(vp_handle* h, int mode, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                          void* out, float* spatial_features, int normalize, void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
+  if (h == nullptr) return VP_ERR_INVALID;
+  uint64_t tk = 0;
+  int rc = host_pipeline(h, mode, video, in_dtype, B, T, H, W, frame_paddings, out, spatial_features, VP_F32, normalize,
+                         static_cast<cudaStream_t>(stream), &tk);
+  if (rc != VP_OK) return rc;
+  CK(cudaEventSynchronize(h->ev_done[tk % vp_handle::kTickets]));
+  CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return VP_OK;
 }
 
 int vp_encoder_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
                             float* out_features, float* spatial_features, void* stream) {
-  return encoder_forward_host_impl(h, video, VP_F32, B, T, H, W, frame_paddings, out_features, spatial_features, stream);
+  return host_sync_call(h, 0, video, VP_F32, B, T, H, W, frame_paddings, out_features, spatial_features, 0, stream);
 }
 
 int vp_encoder_forward_host_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
                                float* out_features, float* spatial_features, void* stream) {
-  return encoder_forward_host_impl(h, video, VP_U8, B, T, H, W, frame_paddings, out_features, spatial_features, stream);
+  return host_sync_call(h, 0, video, VP_U8, B, T, H, W, frame_paddings, out_features, spatial_features, 0, stream);
 }
 
 int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
@@ -1227,15 +1313,33 @@ int vp_clip_video_forward(vp_handle* h, const float* video, int B, int T, int H,
   DeviceScope device_scope(h ? h->device : -1);
   int rc = check_ready(h);
   if (rc != VP_OK) return rc;
+  return clip_video_forward_dev(h, video, VP_F32, B, T, H, W, frame_paddings, normalize, video_emb, spatial_features,
+                                spatiotemporal_features, frame_embeddings, static_cast<cudaStream_t>(stream));
+}
+
+int vp_clip_video_forward_u8(vp_handle* h, const uint8_t* video, int B, int T, int H, int W, const float* frame_paddings,
+                             int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                             float* frame_embeddings, void* stream) {
+  DeviceScope device_scope(h ? h->device : -1);
+  int rc = check_ready(h);
+  if (rc != VP_OK) return rc;
+  return clip_video_forward_dev(h, video, VP_U8, B, T, H, W, frame_paddings, normalize, video_emb, spatial_features,
+                                spatiotemporal_features, frame_embeddings, static_cast<cudaStream_t>(stream));
+}
+
+// callers hold a DeviceScope and have passed check_ready
+static int clip_video_forward_dev(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                                  int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                                  float* frame_embeddings, cudaStream_t st) {
+  int rc;
   if (h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
   if (video == nullptr || video_emb == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const vp_config& c = h->cfg;
   const int D = c.model_dim;
   size_t M = 0;
   // vision_encoder (encoders.py:822-841).  Its output (after temporal_ln) becomes the residual
   // stream of the auxiliary encoder, so LN writes bf16 back into ws_x.
-  rc = encoder_body(h, video, VP_F32, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
+  rc = encoder_body(h, video, in_dtype, B, T, H, W, frame_paddings, spatiotemporal_features, nullptr, true, spatial_features, st, &M);
   if (rc != VP_OK) return rc;
   if (h->check_fp32) {   // the same three stages in float32
     float* xf = static_cast<float*>(h->c_x.p);
@@ -1361,21 +1465,7 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
 
 int vp_clip_video_forward_host(vp_handle* h, const float* video, int B, int T, int H, int W, int normalize, float* video_emb,
                                void* stream) {
-  DeviceScope device_scope(h ? h->device : -1);
-  int rc = check_ready(h);
-  if (rc != VP_OK) return rc;
-  if (video == nullptr || video_emb == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return h->fail(VP_ERR_INVALID, "bad argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t in_elems = (size_t)B * T * H * W * 3;
-  CK(h->ws_io_in.ensure(in_elems * sizeof(float)));
-  CK(h->ws_io_out.ensure((size_t)B * h->cfg.model_dim * sizeof(float)));
-  CK(cudaMemcpyAsync(h->ws_io_in.p, video, in_elems * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = vp_clip_video_forward(h, static_cast<const float*>(h->ws_io_in.p), B, T, H, W, nullptr, normalize,
-                             static_cast<float*>(h->ws_io_out.p), nullptr, nullptr, nullptr, stream);
-  if (rc != VP_OK) return rc;
-  CK(cudaMemcpyAsync(video_emb, h->ws_io_out.p, (size_t)B * h->cfg.model_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return VP_OK;
+  return host_sync_call(h, 1, video, VP_F32, B, T, H, W, nullptr, video_emb, nullptr, normalize, stream);
 }
 
 int vp_clip_text_forward_host(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize,

@@ -112,6 +112,7 @@ class _Module:
         self._loaded_state_id: Optional[int] = None
         self._loaded_state_ref = None
         self._loaded_fingerprint = None
+        self._inflight: Dict[int, Any] = {}
 
     # -- handle -------------------------------------------------------------------------------
     def _vp_config(self) -> _lib.VpConfig:
@@ -228,6 +229,12 @@ class _Module:
         self._bind(variables)
         return self(*args, **kwargs)
 
+    def wait(self, ticket: int) -> None:
+        """Blocks until the asynchronous host call `ticket` (forward_async / embed_video_async) has delivered its results."""
+        _lib.check(_lib.lib().vp_wait(self._ensure_handle(), C.c_uint64(int(ticket))), self._handle)
+        for k in [k for k in self._inflight if k <= ticket]:
+            del self._inflight[k]
+
     def release_workspace(self) -> None:
         """Frees the activation workspace (sized for the largest batch seen so far); weights stay loaded.  The next call
         allocates again: for servers that see one large batch and then go back to small ones."""
@@ -310,20 +317,48 @@ class FactorizedEncoder(_Module):
                                                   _lib.VP_BF16 if bf16_out else _lib.VP_F32, self._stream_ptr()), h)
             outs = {"spatial_features": sp} if want_spatial else {}
             return out, outs
+        ticket, out, outs = self.forward_async(inputs, return_intermediate=return_intermediate, frame_paddings=frame_paddings, out=out)
+        self.wait(ticket)
+        return out, outs
+
+    def forward_async(self, inputs, return_intermediate: bool | Collection[str] = False, frame_paddings=None, out=None,
+                      bf16_features: bool = False):
+        """Host buffers only (extension; the reference's counterpart is JAX's asynchronous dispatch): enqueues the
+        chunk-pipelined H2D copies, the forward and the D2H copies and returns `(ticket, out, outs)` at once; `wait(ticket)`
+        (= block_until_ready) returns when `out` holds the features.  Calls pipeline on the device: the copies of one call
+        overlap the forward of its neighbours, so a loop `t = forward_async(x[i], out=o[i % 2]); wait(prev); prev = t` is bound
+        by the forward alone.  `inputs` (float32 or uint8 frames) and `out` should be page-locked (`pinned_empty`) and must not
+        be touched before `wait` returns.  `bf16_features=True`: `out` is a uint16 array holding bfloat16 bit patterns (numpy
+        has no bfloat16; `torch.from_numpy(out).view(torch.bfloat16)`): half the device-to-host bytes."""
+        lib = _lib.lib()
+        h = self._ensure_handle()
+        if _is_torch(inputs):
+            raise ValueError("forward_async takes host (numpy) buffers; CUDA tensors are already asynchronous through __call__")
+        b, t, hh, ww = self._check_video(inputs)
+        p = self.config["patch_size"]
+        n, d = (hh // p) * (ww // p), self.config["model_dim"]
+        want_spatial = _contains(return_intermediate, "spatial_features")
+        if want_spatial and bf16_features:
+            raise ValueError("spatial_features are float32: not available together with bf16_features")
+        if frame_paddings is not None and tuple(frame_paddings.shape) != (b, t):
+            raise AssertionError("frame_paddings.shape == (b, t)")  # encoders.py:442
         is_u8 = np.asarray(inputs).dtype == np.uint8
         x = np.ascontiguousarray(np.asarray(inputs), dtype=np.uint8 if is_u8 else np.float32)
-        fwd_host = lib.vp_encoder_forward_host_u8 if is_u8 else lib.vp_encoder_forward_host
+        odt = np.uint16 if bf16_features else np.float32
         if out is None:
-            out = np.empty((b, t * n, d), dtype=np.float32)
-        elif out.shape != (b, t * n, d) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
-            raise ValueError(f"out must be a C-contiguous float32 array of shape {(b, t * n, d)}")
+            out = np.empty((b, t * n, d), dtype=odt)
+        elif out.shape != (b, t * n, d) or out.dtype != odt or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a C-contiguous {np.dtype(odt).name} array of shape {(b, t * n, d)}")
         sp = np.empty_like(out) if want_spatial else None
         fp = None if frame_paddings is None else np.ascontiguousarray(np.asarray(frame_paddings), dtype=np.float32)
-        _lib.check(fwd_host(
-            h, x.ctypes.data_as(C.c_void_p), b, t, hh, ww, None if fp is None else fp.ctypes.data_as(C.c_void_p),
-            out.ctypes.data_as(C.c_void_p), None if sp is None else sp.ctypes.data_as(C.c_void_p), None), h)
+        ticket = C.c_uint64(0)
+        _lib.check(lib.vp_encoder_forward_host_async(
+            h, x.ctypes.data_as(C.c_void_p), _lib.VP_U8 if is_u8 else _lib.VP_F32, b, t, hh, ww,
+            None if fp is None else fp.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+            None if sp is None else sp.ctypes.data_as(C.c_void_p), _lib.VP_BF16 if bf16_features else _lib.VP_F32, None, C.byref(ticket)), h)
+        self._inflight[ticket.value] = (x, fp, out, sp)     # keeps the host buffers alive until wait()
         outs = {"spatial_features": sp} if want_spatial else {}
-        return out, outs
+        return ticket.value, out, outs
 
 
 class FactorizedVideoCLIP(_Module):
@@ -360,7 +395,7 @@ class FactorizedVideoCLIP(_Module):
                         ptr("spatial_features"), ptr("spatiotemporal_features"), ptr("frame_embeddings"), self._stream_ptr()), h)
                 outs.update(bufs)
             else:
-                if names or frame_paddings is not None:
+                if names:
                     # host path with intermediates: stage through torch device buffers
                     import torch
                     xv = torch.from_numpy(np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)).cuda(self.device_index)
@@ -369,10 +404,8 @@ class FactorizedVideoCLIP(_Module):
                     video_emb = v.cpu().numpy()
                     outs.update({k: a.cpu().numpy() for k, a in o.items()})
                 else:
-                    x = np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)
-                    video_emb = np.empty((b, d), dtype=np.float32)
-                    _lib.check(lib.vp_clip_video_forward_host(h, x.ctypes.data_as(C.c_void_p), b, t, hh, ww, int(bool(normalize)),
-                                                              video_emb.ctypes.data_as(C.c_void_p), None), h)
+                    ticket, video_emb = self.embed_video_async(inputs, frame_paddings=frame_paddings, normalize=normalize)
+                    self.wait(ticket)
         if text_token_ids is not None:
             assert text_paddings is not None, "Text paddings are required."  # encoders.py:888
             if text_token_ids.ndim != 2 or tuple(text_paddings.shape) != tuple(text_token_ids.shape):
@@ -393,6 +426,35 @@ class FactorizedVideoCLIP(_Module):
                 _lib.check(lib.vp_clip_text_forward_host(h, ids.ctypes.data_as(C.c_void_p), pad.ctypes.data_as(C.c_void_p), q, length,
                                                          int(bool(normalize)), text_emb.ctypes.data_as(C.c_void_p), None), h)
         return video_emb, text_emb, outs
+
+
+    # (method of FactorizedVideoCLIP, attached below)
+def _embed_video_async(self, inputs, frame_paddings=None, normalize: bool = True, out=None):
+    """Host buffers only (extension): pooled video embeddings `[B, D]` of float32 or uint8 clips through the chunk-pipelined
+    asynchronous entry point (vp_clip_video_forward_host_async); returns `(ticket, out)`, `wait(ticket)` for the result.
+    Consecutive calls overlap their host-to-device copies with the neighbouring call's forward."""
+    lib = _lib.lib()
+    h = self._ensure_handle()
+    b, t, hh, ww = self._check_video(inputs)
+    d = self.config["model_dim"]
+    if frame_paddings is not None and tuple(frame_paddings.shape) != (b, t):
+        raise AssertionError("frame_paddings.shape == (b, t)")  # encoders.py:442
+    is_u8 = np.asarray(inputs).dtype == np.uint8
+    x = np.ascontiguousarray(np.asarray(inputs), dtype=np.uint8 if is_u8 else np.float32)
+    if out is None:
+        out = np.empty((b, d), dtype=np.float32)
+    elif out.shape != (b, d) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out must be a C-contiguous float32 array of shape {(b, d)}")
+    fp = None if frame_paddings is None else np.ascontiguousarray(np.asarray(frame_paddings), dtype=np.float32)
+    ticket = C.c_uint64(0)
+    _lib.check(lib.vp_clip_video_forward_host_async(
+        h, x.ctypes.data_as(C.c_void_p), _lib.VP_U8 if is_u8 else _lib.VP_F32, b, t, hh, ww,
+        None if fp is None else fp.ctypes.data_as(C.c_void_p), int(bool(normalize)), out.ctypes.data_as(C.c_void_p), None, C.byref(ticket)), h)
+    self._inflight[ticket.value] = (x, fp, out)
+    return ticket.value, out
+
+
+FactorizedVideoCLIP.embed_video_async = _embed_video_async
 
 
 class FactorizedVideoClassifier(_Module):
