@@ -47,5 +47,38 @@ for B in (1, 2, 4):
     for _ in range(20):
         model(vp_in, out=out)
     host_ms = (time.perf_counter() - t0) / 20 * 1e3
-    print(f"{name} B={B}: device back-to-back {dev_ms:.3f} ms ({B / dev_ms * 1e3:.0f} clips/s, {launches} launches), "
+    print(f"[graphs {'off' if os.environ.get('VP_GRAPHS') == '0' else 'on'}] {name} B={B}: device back-to-back {dev_ms:.3f} ms ({B / dev_ms * 1e3:.0f} clips/s, {launches} launches), "
           f"one at a time {sync_ms:.3f} ms, host numpy->numpy (pinned) {host_ms:.3f} ms")
+
+# the reference's own benchmark shape (scripts/benchmark_performance.py:70-94): video-text model, 1 clip + 3 text queries
+if len(sys.argv) <= 1 or sys.argv[1] == "base":
+    lvt = vp.get_model("videoprism_lvt_public_v1_base")
+    lvt.load_state(vp.synthetic_state(lvt, seed=1234))
+    v1 = torch.from_numpy(np.random.default_rng(0).random((1, 16, 288, 288, 3), dtype=np.float32)).cuda()
+    ids = torch.from_numpy(np.random.default_rng(2).integers(1, 32000, (3, 64), dtype=np.int32)).cuda()
+    pad = torch.zeros((3, 64), device="cuda"); pad[:, 12:] = 1.0
+    ve = torch.empty((1, 768), device="cuda"); te = torch.empty((3, 768), device="cuda")
+    import videoprism_b200._lib as _L
+    lib = _L.lib()
+    h = lvt._ensure_handle()
+    st = int(torch.cuda.current_stream().cuda_stream)
+
+    def lvt_pass():   # fixed output buffers: the call sequence a serving loop makes (and the one the graph cache keys on)
+        assert lib.vp_clip_video_forward(h, v1.data_ptr(), 1, 16, 288, 288, None, 1, ve.data_ptr(), None, None, None, st) == 0
+        assert lib.vp_clip_text_forward(h, ids.data_ptr(), pad.data_ptr(), 3, 64, 1, te.data_ptr(), st) == 0
+    for _ in range(5):
+        lvt_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        lvt_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        lvt_pass()
+        torch.cuda.synchronize()
+    sync_ms = (time.perf_counter() - t0) / 50 * 1e3
+    print(f"videoprism_lvt_public_v1_base 1 clip + 3 queries: device back-to-back {e0.elapsed_time(e1) / 50:.3f} ms, one at a time {sync_ms:.3f} ms "
+          f"(graphs {'off' if os.environ.get('VP_GRAPHS') == '0' else 'on'})")

@@ -43,12 +43,14 @@ std::string g_create_error;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  uint64_t* gen = nullptr;   // bumped whenever the buffer moves: captured CUDA graphs that hold the old pointer are stale
   // Grows (never shrinks) the buffer.  cudaFree / cudaMalloc synchronise with the device, so a buffer still in use by
   // queued work is never pulled away; `zero` clears a NEW allocation on the caller's stream `st`, i.e. ordered before
   // the kernels the caller enqueues next on that stream (a memset on the legacy default stream would not be ordered
   // against cudaStreamNonBlocking streams).
   cudaError_t ensure(size_t n, bool zero = false, cudaStream_t st = nullptr) {
     if (n <= bytes) return cudaSuccess;
+    if (gen) ++*gen;
     if (p) cudaFree(p);
     p = nullptr; bytes = 0;
     cudaError_t e = cudaMalloc(&p, n);
@@ -57,7 +59,17 @@ struct DevBuf {
     if (zero) e = cudaMemsetAsync(p, 0, n, st);
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; if (gen) ++*gen; }
+};
+
+// A forward captured as a CUDA graph: replaying it costs one launch instead of ~84 (+ ~250 tensor-map encodes), which is
+// what a 1-clip forward is bound by.  The key holds everything the captured launches depend on (entry, shapes, dtypes and
+// every caller pointer); `gen` is the workspace generation at capture time.
+struct GraphEntry {
+  std::vector<uint64_t> key;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  uint64_t gen = 0, stamp = 0;
 };
 
 struct StackWeights {
@@ -148,6 +160,12 @@ struct vp_handle {
   cudaEvent_t ev_done[kTickets] = {};   // ev_done[t % kTickets]: results of the call with ticket t are in the caller's buffers
   uint64_t next_ticket = 1;
   int host_chunk_clips = 0;   // 0 = automatic
+  // CUDA graphs (VP_GRAPHS=0 disables): the second call with a given key is captured, later ones replay
+  bool use_graphs = true, capturing = false;
+  uint64_t ws_generation = 0, graph_clock = 0;
+  std::vector<GraphEntry> graphs;
+  std::vector<std::vector<uint64_t>> graph_seen, graph_bad;
+  cudaStream_t s_cap = nullptr;
   size_t stats_stride = 0;    // floats between the two LayerNorm-statistics buffers
 
   int fail(int code, const char* fmt, ...) {
@@ -460,6 +478,7 @@ int prepare_pos_tables(vp_handle* h, int T, int gh, int gw, cudaStream_t st) {
             for (int d = 0; d < D; ++d) tab[((size_t)y * gw + o) * D + d] += w * tmp[((size_t)y * c.pos_emb_w + i) * D + d];
           }
     }
+    ++h->ws_generation;   // the tables move: captured graphs are stale
     if (h->d_spatial_pos) { cudaFree(h->d_spatial_pos); h->d_spatial_pos = nullptr; }
     CK(cudaMalloc(&h->d_spatial_pos, tab.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->d_spatial_pos, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -485,6 +504,7 @@ int prepare_pos_tables(vp_handle* h, int T, int gh, int gw, cudaStream_t st) {
           for (int d = 0; d < D; ++d) tab[(size_t)o * D + d] += w * h->h_temporal_pos[(size_t)i * D + d];
         }
     }
+    ++h->ws_generation;
     if (h->d_temporal_pos) { cudaFree(h->d_temporal_pos); h->d_temporal_pos = nullptr; }
     CK(cudaMalloc(&h->d_temporal_pos, tab.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->d_temporal_pos, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -567,6 +587,7 @@ int prepare_pe(vp_handle* h, int L, cudaStream_t st) {
       pe[(size_t)p * D + i] = sinf(stime);
       pe[(size_t)p * D + nts + i] = cosf(stime);
     }
+  ++h->ws_generation;
   if (h->d_pe) { cudaFree(h->d_pe); h->d_pe = nullptr; }
   CK(cudaMalloc(&h->d_pe, pe.size() * sizeof(float)));
   CK(cudaMemcpyAsync(h->d_pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -826,6 +847,70 @@ int pool_f32(vp_handle* h, const float* x, int num_seq, int S, int normalize, fl
   return VP_OK;
 }
 
+// Runs `body(stream)` (a fixed sequence of launches determined by `key`) on `st`, through a cached CUDA graph when there is
+// one.  First call with a key: eager (it sizes the workspace, grants shared memory, uploads tables).  Second call: captured
+// on the handle's private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
+// and launched into `st`.  Later calls: one cudaGraphLaunch.  Anything that moves a buffer a graph points into bumps
+// ws_generation and the stale graphs are dropped.  Tracing (one event after every launch) and nested calls run eagerly.
+template <typename Body>
+int run_graphed(vp_handle* h, cudaStream_t st, const std::vector<uint64_t>& key, Body&& body) {
+  if (!h->use_graphs || h->trace_on || h->capturing) return body(st);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return body(st); }   // the caller is capturing
+  for (size_t i = 0; i < h->graphs.size();) {   // drop stale graphs
+    if (h->graphs[i].gen != h->ws_generation) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
+    else ++i;
+  }
+  for (GraphEntry& g : h->graphs)
+    if (g.key == key) {
+      g.stamp = ++h->graph_clock;
+      CK(cudaGraphLaunch(g.exec, st));
+      h->launches += g.launches;
+      return VP_OK;
+    }
+  if (std::find(h->graph_bad.begin(), h->graph_bad.end(), key) != h->graph_bad.end()) return body(st);
+  if (std::find(h->graph_seen.begin(), h->graph_seen.end(), key) == h->graph_seen.end()) {
+    if (h->graph_seen.size() >= 64) h->graph_seen.erase(h->graph_seen.begin());
+    h->graph_seen.push_back(key);
+    return body(st);
+  }
+  if (h->s_cap == nullptr) CK(cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
+  const uint64_t gen0 = h->ws_generation;
+  const int64_t l0 = h->launches;
+  if (cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return body(st); }
+  h->capturing = true;
+  const int rc = body(h->s_cap);
+  h->capturing = false;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ec = cudaStreamEndCapture(h->s_cap, &graph);
+  const int64_t captured = h->launches - l0;
+  h->launches = l0;
+  cudaGraphExec_t exec = nullptr;
+  if (rc != VP_OK || ec != cudaSuccess || graph == nullptr || gen0 != h->ws_generation ||
+      cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != VP_OK) return rc;
+    h->graph_bad.push_back(key);
+    return body(st);
+  }
+  cudaGraphDestroy(graph);
+  if (h->graphs.size() >= 32) {   // least recently used goes
+    size_t lru = 0;
+    for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+    cudaGraphExecDestroy(h->graphs[lru].exec);
+    h->graphs.erase(h->graphs.begin() + lru);
+  }
+  GraphEntry g;
+  g.key = key; g.exec = exec; g.launches = captured; g.gen = gen0; g.stamp = ++h->graph_clock;
+  h->graphs.push_back(g);
+  CK(cudaGraphLaunch(exec, st));
+  h->launches += captured;
+  return VP_OK;
+}
+
+static inline uint64_t key_ptr(const void* p) { return static_cast<uint64_t>(reinterpret_cast<uintptr_t>(p)); }
+
 // Selects the handle's device for the duration of one C-ABI call and restores the caller's current device afterwards: an
 // entry point must not change the calling thread's device as a side effect (a destructor running vp_destroy for a model
 // on cuda:0 would otherwise silently move the caller off cuda:1).
@@ -853,8 +938,8 @@ int check_ready(vp_handle* h) {   // callers hold a DeviceScope on h->device
 
 // Shared body of the encoder forward.  Leaves the final (pre-temporal_ln) residual stream in ws_x and
 // writes LN outputs where requested.  Returns the token count through *M_out.
-int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
-                 bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
+int encoder_body_eager(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
+                       bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
   if (h->check_fp32) return encoder_body_f32(h, video, in_dtype, B, T, H, W, frame_pad, out_f32, out_bf16, final_ln_in_place, spatial_f32, st, M_out);
   const vp_config& c = h->cfg;
   const int D = c.model_dim, P = c.patch_size;
@@ -921,6 +1006,19 @@ int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, in
   return VP_OK;
 }
 
+int encoder_body(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_pad, float* out_f32,
+                 bf16* out_bf16, bool final_ln_in_place, float* spatial_f32, cudaStream_t st, size_t* M_out) {
+  const int P = h->cfg.patch_size;
+  if (B <= 0 || T <= 0 || P <= 0 || H <= 0 || W <= 0 || H % P || W % P || H != W)   // the eager body reports the precise reason
+    return encoder_body_eager(h, video, in_dtype, B, T, H, W, frame_pad, out_f32, out_bf16, final_ln_in_place, spatial_f32, st, M_out);
+  if (M_out) *M_out = (size_t)B * T * (H / P) * (W / P);
+  const std::vector<uint64_t> key = {1, (uint64_t)in_dtype, (uint64_t)B, (uint64_t)T, (uint64_t)H, (uint64_t)W, key_ptr(video), key_ptr(frame_pad),
+                                     key_ptr(out_f32), key_ptr(out_bf16), (uint64_t)final_ln_in_place, key_ptr(spatial_f32), (uint64_t)h->fuse_ln};
+  return run_graphed(h, st, key, [&](cudaStream_t s) {
+    return encoder_body_eager(h, video, in_dtype, B, T, H, W, frame_pad, out_f32, out_bf16, final_ln_in_place, spatial_f32, s, nullptr);
+  });
+}
+
 }  // namespace
 
 // ===================================================================== C ABI
@@ -970,6 +1068,12 @@ int vp_create_ex(const vp_config* cfg, int device, unsigned flags, vp_handle** o
   h->check_fp32 = (flags & VP_FLAG_CHECK_FP32) != 0;
   if (const char* ev = getenv("VP_HOST_CHUNK_CLIPS")) h->host_chunk_clips = atoi(ev);   // tuning knob of the host pipeline
   if (const char* ev = getenv("VP_FUSE_LN")) h->fuse_ln = atoi(ev) != 0;
+  if (const char* ev = getenv("VP_GRAPHS")) h->use_graphs = atoi(ev) != 0;
+  {
+    DevBuf* bufs[] = {&h->ws_x, &h->ws_n, &h->ws_qkv, &h->ws_u, &h->ws_patch, &h->ws_misc, &h->ws_io_in, &h->ws_io_out, &h->ws_pool, &h->ws_stats,
+                      &h->c_x, &h->c_n, &h->c_qkv, &h->c_u, &h->c_patch, &h->c_pool};
+    for (DevBuf* b : bufs) b->gen = &h->ws_generation;
+  }
   if (cudaGetDevice(&h->device) != cudaSuccess || h->device != device) {
     g_create_error = "cannot select device " + std::to_string(device);
     delete h;
@@ -999,6 +1103,8 @@ void vp_destroy(vp_handle* h) {
   DeviceScope device_scope(h->device);
   for (void* p : h->owned) cudaFree(p);
   for (auto& t : h->trace) cudaEventDestroy(t.second);
+  for (GraphEntry& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->s_cap) cudaStreamDestroy(h->s_cap);
 
   if (h->d_spatial_pos) cudaFree(h->d_spatial_pos);
   if (h->d_spatial_pos_bf16) cudaFree(h->d_spatial_pos_bf16);
@@ -1327,10 +1433,26 @@ int vp_clip_video_forward_u8(vp_handle* h, const uint8_t* video, int B, int T, i
                                 spatiotemporal_features, frame_embeddings, static_cast<cudaStream_t>(stream));
 }
 
+static int clip_video_forward_eager(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                                    int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                                    float* frame_embeddings, cudaStream_t st);
+
 // callers hold a DeviceScope and have passed check_ready
 static int clip_video_forward_dev(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
                                   int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
                                   float* frame_embeddings, cudaStream_t st) {
+  const std::vector<uint64_t> key = {2, (uint64_t)in_dtype, (uint64_t)B, (uint64_t)T, (uint64_t)H, (uint64_t)W, key_ptr(video), key_ptr(frame_paddings),
+                                     (uint64_t)normalize, key_ptr(video_emb), key_ptr(spatial_features), key_ptr(spatiotemporal_features),
+                                     key_ptr(frame_embeddings), (uint64_t)h->fuse_ln};
+  return run_graphed(h, st, key, [&](cudaStream_t s) {
+    return clip_video_forward_eager(h, video, in_dtype, B, T, H, W, frame_paddings, normalize, video_emb, spatial_features,
+                                    spatiotemporal_features, frame_embeddings, s);
+  });
+}
+
+static int clip_video_forward_eager(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
+                                    int normalize, float* video_emb, float* spatial_features, float* spatiotemporal_features,
+                                    float* frame_embeddings, cudaStream_t st) {
   int rc;
   if (h->cfg.kind != VP_KIND_CLIP) return h->fail(VP_ERR_INVALID, "handle is not a video-text (CLIP) model");
   if (video == nullptr || video_emb == nullptr) return h->fail(VP_ERR_INVALID, "null video / output pointer");
@@ -1411,6 +1533,9 @@ int vp_classifier_forward(vp_handle* h, const float* video, int B, int T, int H,
   return VP_OK;
 }
 
+static int clip_text_forward_eager(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize, float* text_emb,
+                                   cudaStream_t st);
+
 int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize, float* text_emb,
                          void* stream) {
   DeviceScope device_scope(h ? h->device : -1);
@@ -1420,7 +1545,15 @@ int vp_clip_text_forward(vp_handle* h, const int32_t* ids, const float* paddings
   if (ids == nullptr || text_emb == nullptr) return h->fail(VP_ERR_INVALID, "null ids / output pointer");
   if (paddings == nullptr) return h->fail(VP_ERR_INVALID, "Text paddings are required. (encoders.py:888)");
   if (Q <= 0 || L <= 0) return h->fail(VP_ERR_INVALID, "empty text batch");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const std::vector<uint64_t> key = {3, (uint64_t)Q, (uint64_t)L, key_ptr(ids), key_ptr(paddings), (uint64_t)normalize, key_ptr(text_emb), (uint64_t)h->fuse_ln};
+  return run_graphed(h, static_cast<cudaStream_t>(stream), key, [&](cudaStream_t s) {
+    return clip_text_forward_eager(h, ids, paddings, Q, L, normalize, text_emb, s);
+  });
+}
+
+static int clip_text_forward_eager(vp_handle* h, const int32_t* ids, const float* paddings, int Q, int L, int normalize, float* text_emb,
+                                   cudaStream_t st) {
+  int rc;
   const vp_config& c = h->cfg;
   const int D = c.model_dim, S = L + 1;
   const size_t M = (size_t)Q * S;
