@@ -29,6 +29,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+try:
+    _ORIG_AFFINITY = set(os.sched_getaffinity(0))   # bind_to_gpu_numa_node narrows it; the CPU-baseline legs get it back
+except AttributeError:
+    _ORIG_AFFINITY = None
+
+
+def _restore_affinity():
+    if _ORIG_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _ORIG_AFFINITY)
+        except OSError:
+            pass
+
+
 GF_PER_CLIP = {"base": 973.29, "large": 2998.52}          # BASELINE.md §3 (2*M*N*K per GEMM + 4*S^2*dh*H per sequence)
 MODEL_NAME = {"base": "videoprism_public_v1_base", "large": "videoprism_public_v1_large"}
 
@@ -109,26 +123,66 @@ class ClockSampler:
                 "power_w_max": max(power_load or power), "reasons_window": "first warm-up step .. end of the timed region"}
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def _smi_cpu_affinity(bus_id: str):
+    """CPU affinity of the GPU with this PCI bus id from `nvidia-smi topo -m` (the 'CPU Affinity' column), or None."""
+    q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20)
+    index = None
+    for ln in q.stdout.splitlines():
+        idx, _, bid = ln.partition(",")
+        if bid.strip().lower().endswith(bus_id.lower()):   # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            index = int(idx)
+    if index is None:
+        return None
+    topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+    header = next((ln for ln in topo if "CPU Affinity" in ln), None)
+    if header is None:
+        return None
+    col = [c.strip() for c in header.split("\t")].index("CPU Affinity")
+    for ln in topo:
+        cells = [c.strip() for c in ln.split("\t")]
+        if cells and cells[0] == f"GPU{index}" and len(cells) > col and cells[col] and cells[col][0].isdigit():
+            return _parse_cpulist(cells[col])
+    return None
+
+
 def bind_to_gpu_numa_node(local: int):
-    """Pins this rank (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA node its
-    GPU hangs off, so that 8 ranks' H2D / D2H streams do not cross the socket interconnect.  Returns the node or None."""
+    """Pins this rank (and the pinned host buffers it allocates afterwards: first touch) to the CPUs next to its GPU (sysfs
+    numa_node of the PCI device, else the 'CPU Affinity' column of `nvidia-smi topo -m`), so that 8 ranks' H2D / D2H
+    streams do not cross the socket interconnect.  Returns a description of what was done, or None (nothing changed)."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(local)
         bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
+        cpus, how = None, None
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            if node >= 0:
+                with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                    cpus, how = _parse_cpulist(f.read()), f"numa node {node} (sysfs)"
+        except Exception:
+            cpus = None
+        if not cpus:
+            cpus = _smi_cpu_affinity(bus)
+            how = "nvidia-smi topo CPU affinity"
+        if not cpus:
             return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                a, _, b = part.partition("-")
-                cpus.update(range(int(a), int(b or a) + 1))
-        allowed = cpus & set(os.sched_getaffinity(0))
-        if allowed:
+        current = set(os.sched_getaffinity(0))
+        allowed = cpus & current
+        if allowed and allowed != current:
             os.sched_setaffinity(0, allowed)
-            return node
+            return f"{how}: {len(allowed)} cpus"
     except Exception:
         pass
     return None
@@ -156,6 +210,7 @@ def cpu_oracle_clips_per_s(model: str, steps: int, warmup: int, budget_s: float)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import videoprism_oracle as O
+    _restore_affinity()
     # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would make this a 1-thread run)
     try:
         n_cores = len(os.sched_getaffinity(0))
@@ -207,6 +262,7 @@ def cpu_oracle_retrieval(model: str, budget_s: float):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import videoprism_oracle as O
+    _restore_affinity()
     try:
         n_cores = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -336,9 +392,10 @@ def run_retrieval(args):
     roof, cpu = None, None
     if rank == 0:
         D, F, Hh = model.config["model_dim"], model.config["mlp_dim"], model.config["num_heads"]
+        # rank 0 ALONE runs these extra steps, so they must not contain the collective: the forward only (video + text)
         model.trace(True)
         for _ in range(2):
-            step()
+            model(video, ids, pad)
         rows = model.trace_report()
         model.trace(False)
         total_ms = [r for r in rows if r[0] == "TOTAL"][0][2]
@@ -381,6 +438,7 @@ def run_retrieval(args):
             "queries_per_s": n_q / (ms / 1e3), "similarity_shape": list(sim.shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu}), flush=True)
     if world > 1:
+        dist.barrier()   # rank 0's trace / CPU-baseline legs run alone; nobody leaves before it is done
         dist.destroy_process_group()
 
 
