@@ -110,7 +110,8 @@ VP_API int vp_finalize(vp_handle* h);                             /* checks comp
 /* -- FactorizedEncoder.__call__ (videoprism/encoders.py:411-456, encode_with_patches :458-580).
  *    video [B,T,H,W,3] fp32 device memory, values as the reference expects ([0,1]).
  *    out_features [B, T*N, D] (out_dtype VP_F32 or VP_BF16).  spatial_features may be NULL, else
- *    receives outputs['spatial_features'] [B, T*N, D] in out_dtype.  frame_paddings may be NULL, else
+ *    receives outputs['spatial_features'] [B, T*N, D] in float32 (it needs out_dtype == VP_F32: asking
+ *    for it together with VP_BF16 returns VP_ERR_UNSUPPORTED).  frame_paddings may be NULL, else
  *    [B,T] fp32 device memory (1 = padded frame).  `stream` is a cudaStream_t. */
 VP_API int vp_encoder_forward(vp_handle* h, const float* video, int B, int T, int H, int W, const float* frame_paddings,
                        void* out_features, void* spatial_features, int out_dtype, void* stream);

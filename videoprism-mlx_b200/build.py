@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvideoprism_b200.so")
-SOURCES = ["gemm_tcgen05.cu", "check_fp32.cu", "attention.cu", "attention_tcgen05.cu", "attention_long_tcgen05.cu", "attention_kloop_tcgen05.cu", "elementwise.cu", "ingest.cu", "pooling.cu", "engine.cu"]
+SOURCES = ["gemm_tcgen05.cu", "check_fp32.cu", "attention.cu", "attention_kloop_tcgen05.cu", "elementwise.cu", "ingest.cu", "pooling.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -6,8 +6,8 @@
 //   attn_flash_kernel : 64 queries per CTA (4 warps x 16 rows), K/V streamed in 64-key tiles through a
 //                       double-buffered cp.async ring (spatial S=256, auxiliary S=4096, text S=65)
 //   attn_small_kernel : S <= 16 (temporal stack): one warp per (sequence, head), 4 heads per CTA
-// Tensor work is mma.sync m16n8k16 bf16 with fp32 accumulation; the tcgen05 variant for the
-// S=256 spatial case lives in attention_tcgen05.cu.
+// Tensor work is mma.sync m16n8k16 bf16 with fp32 accumulation; the tcgen05 kernel for the unmasked
+// S % 256 == 0, dh = 64 cases (spatial stack, auxiliary encoder) lives in attention_kloop_tcgen05.cu.
 #include <math_constants.h>
 
 #include <stdlib.h>
@@ -341,31 +341,9 @@ __global__ void __launch_bounds__(256) attn_uniform_rows_kernel(const AttnArgs a
 
 }  // namespace
 
-cudaError_t launch_attention_tcgen05(cudaStream_t s, const AttnArgs& a);
-cudaError_t launch_attention_long_tcgen05(cudaStream_t s, const AttnArgs& a);
+// attention_kloop_tcgen05.cu: tcgen05 / TMEM kernel for unmasked sequences with S % 256 == 0 and dh = 64 (the spatial stack
+// and the auxiliary encoder); returns cudaErrorNotSupported for anything else, which then runs on the kernels of this file
 cudaError_t launch_attention_kloop_tcgen05(cudaStream_t s, const AttnArgs& a);
-
-namespace {
-// VP_ATTN_KERNEL: 2 (default) = key-loop kernel for every S % 256 == 0; 1 = key-loop kernel for S >= 512 only, whole-row
-// kernel for S = 256; 0 = the round-1 pair (whole-row S = 256 kernel + round-1 key-loop kernel)
-int attn_kernel_choice() {
-  static int v = [] {
-    const char* e = getenv("VP_ATTN_KERNEL");
-    return e ? atoi(e) : 2;
-  }();
-  return v;
-}
-cudaError_t launch_attention_tc(cudaStream_t s, const AttnArgs& a) {
-  const int choice = attn_kernel_choice();
-  if (choice >= 2 || (choice == 1 && a.S >= 512)) {
-    const cudaError_t e = launch_attention_kloop_tcgen05(s, a);
-    if (e != cudaErrorNotSupported) return e;
-  }
-  const cudaError_t e = launch_attention_tcgen05(s, a);   // S = 256, dh = 64, unmasked: the spatial stack
-  if (e != cudaErrorNotSupported) return e;
-  return launch_attention_long_tcgen05(s, a);             // S = 512, 768, ... unmasked (round-1 key-loop kernel)
-}
-}  // namespace
 
 cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (a.num_seq <= 0 || a.S <= 0) return cudaSuccess;
@@ -376,7 +354,7 @@ cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
   if (!a.force_mma_sync && a.key_pad != nullptr && a.pad_whole_seq && !a.causal) {
     AttnArgs b = a;
     b.key_pad = nullptr;
-    cudaError_t e = launch_attention_tc(s, b);   // unmasked fast path on every sequence ...
+    cudaError_t e = launch_attention_kloop_tcgen05(s, b);   // unmasked fast path on every sequence ...
     if (e == cudaSuccess) {                           // ... then the fully padded sequences get the uniform-softmax result
       attn_uniform_rows_kernel<<<dim3(a.num_seq, a.heads), 256, 0, s>>>(a);
       if (a.launched) *a.launched = 2;
@@ -385,7 +363,7 @@ cudaError_t launch_attention(cudaStream_t s, const AttnArgs& a) {
     if (e != cudaErrorNotSupported) return e;
   }
   if (!a.force_mma_sync) {
-    const cudaError_t e = launch_attention_tc(s, a);   // unmasked, dh = 64, S % 256 == 0: spatial stack / auxiliary encoder
+    const cudaError_t e = launch_attention_kloop_tcgen05(s, a);   // unmasked, dh = 64, S % 256 == 0: spatial stack / auxiliary encoder
     if (e != cudaErrorNotSupported) return e;
   }
   if (a.S <= 16) {

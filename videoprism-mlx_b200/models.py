@@ -133,6 +133,10 @@ class _Module:
             allowed = ("pre", "primer_hybrid") if self._kind == _lib.VP_KIND_CLIP else ("pre",)
             if policy not in allowed:
                 raise NotImplementedError(f"norm_policy={policy!r} is not implemented (supported here: {allowed})")
+            if self._kind == _lib.VP_KIND_CLIP and not self.config.get("enable_causal_atten", True):
+                # encoders.py:682,:751: the text tower's StackedTransformer takes this flag; every released configuration sets
+                # it (models.py:116-161) and the device path's text attention is causal, so the other value is refused loudly
+                raise NotImplementedError("enable_causal_atten=False (a non-causal text tower) is not implemented")
             lib = _lib.lib()
             cfg = self._vp_config()
             h = C.c_void_p()
@@ -330,11 +334,11 @@ class FactorizedEncoder(_Module):
         by the forward alone.  `inputs` (float32 or uint8 frames) and `out` should be page-locked (`pinned_empty`) and must not
         be touched before `wait` returns.  `bf16_features=True`: `out` is a uint16 array holding bfloat16 bit patterns (numpy
         has no bfloat16; `torch.from_numpy(out).view(torch.bfloat16)`): half the device-to-host bytes."""
-        lib = _lib.lib()
-        h = self._ensure_handle()
         if _is_torch(inputs):
             raise ValueError("forward_async takes host (numpy) buffers; CUDA tensors are already asynchronous through __call__")
         b, t, hh, ww = self._check_video(inputs)
+        lib = _lib.lib()
+        h = self._ensure_handle()
         p = self.config["patch_size"]
         n, d = (hh // p) * (ww // p), self.config["model_dim"]
         want_spatial = _contains(return_intermediate, "spatial_features")
