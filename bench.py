@@ -135,7 +135,10 @@ def _parse_cpulist(text: str):
 
 
 def _smi_cpu_affinity(bus_id: str):
-    """CPU affinity of the GPU with this PCI bus id from `nvidia-smi topo -m` (the 'CPU Affinity' column), or None."""
+    """CPU affinity of the GPU with this PCI bus id from `nvidia-smi topo -m`, or None.  The row of GPU<i> holds link types
+    (X, NV18, SYS, PIX, NODE, PHB ...) and then the 'CPU Affinity' cpulist ("0-55,112-167"), the 'NUMA Affinity' node list
+    ("0") and the GPU NUMA id: the CPU affinity is the first cpulist-shaped cell that names at least 8 CPUs."""
+    import re
     q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20)
     index = None
     for ln in q.stdout.splitlines():
@@ -145,14 +148,16 @@ def _smi_cpu_affinity(bus_id: str):
     if index is None:
         return None
     topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
-    header = next((ln for ln in topo if "CPU Affinity" in ln), None)
-    if header is None:
-        return None
-    col = [c.strip() for c in header.split("\t")].index("CPU Affinity")
+    shape = re.compile(r"^\d+(-\d+)?(,\d+(-\d+)?)*$")
     for ln in topo:
-        cells = [c.strip() for c in ln.split("\t")]
-        if cells and cells[0] == f"GPU{index}" and len(cells) > col and cells[col] and cells[col][0].isdigit():
-            return _parse_cpulist(cells[col])
+        cells = [c for c in re.split(r"[\t ]+", ln.strip()) if c]
+        if not cells or cells[0] != f"GPU{index}":
+            continue
+        for c in cells[1:]:
+            if shape.match(c):
+                cpus = _parse_cpulist(c)
+                if len(cpus) >= 8:
+                    return cpus
     return None
 
 
@@ -180,7 +185,7 @@ def bind_to_gpu_numa_node(local: int):
             return None
         current = set(os.sched_getaffinity(0))
         allowed = cpus & current
-        if allowed and allowed != current:
+        if len(allowed) >= 4 and allowed != current:   # never squeeze a rank onto a handful of cores on a parsing accident
             os.sched_setaffinity(0, allowed)
             return f"{how}: {len(allowed)} cpus"
     except Exception:
@@ -582,6 +587,14 @@ def main():
         e2e["uint8_frames_bf16_features"] = {
             "value": timed(lambda i: model.forward_async(u8, out=out16[i & 1], bf16_features=True)[0]), "unit": "clips/s",
             "h2d_bytes_per_step": b_local * clip_bytes // 4, "d2h_bytes_per_step": out_bytes // 2}
+
+        # bytes per second that cross between host memory and the GPUs, all ranks together: at 8 ranks this (one host's
+        # memory / PCIe complex), not the forward, is what bounds the float32-in / float32-out variant
+        def _host_gbs(d):
+            return (d["h2d_bytes_per_step"] + d["d2h_bytes_per_step"]) * world * (d["value"] / args.global_batch) / 1e9
+        e2e["host_copy_gbs_all_ranks"] = _host_gbs(e2e)
+        for k in ("blocking_call", "uint8_frames", "uint8_frames_bf16_features"):
+            e2e[k]["host_copy_gbs_all_ranks"] = _host_gbs(e2e[k])
 
     # ---- roofline of the dominant kernel (FFN1 GEMM: folded LayerNorm + GELU epilogue), timed IN SITU: the engine
     # records a CUDA event after every launch on the launch stream (vp_trace), a few more steps of the same workload
