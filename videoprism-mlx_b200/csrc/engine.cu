@@ -156,6 +156,8 @@ struct vp_handle {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   bool comp_rec[2] = {false, false}, out_rec[2] = {false, false};   // ev_comp / ev_out of the slot have been recorded at least once
   uint64_t chunk_seq = 0;     // chunks enqueued so far, over ALL host calls: slot = chunk_seq & 1, so consecutive calls pipeline
+  size_t pipe_in_stride = 0, pipe_out_stride = 0;   // bytes between the two staging slots: only ever grow (see host_pipeline)
+  int pipe_last_mode = -1;    // the output staging buffer is laid out per mode (features: two slots; embeddings: one block)
   static constexpr int kTickets = 8;
   cudaEvent_t ev_done[kTickets] = {};   // ev_done[t % kTickets]: results of the call with ticket t are in the caller's buffers
   uint64_t next_ticket = 1;
@@ -1304,8 +1306,19 @@ static int host_pipeline(vp_handle* h, int mode, const void* video_v, int in_dty
   const int nchunks = (int)sizes.size();
   int chunk = 0;
   for (int c : sizes) chunk = c > chunk ? c : chunk;
-  const size_t in_stride = ((size_t)chunk * clip_in * esz + 255) / 256 * 256;
-  const size_t out_stride = mode == 0 ? ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256 : 0;
+  // The two staging slots of a buffer are `stride` bytes apart, and calls of DIFFERENT batch sizes may be in flight together
+  // (asynchronous entry points), so the stride must not depend on the call: it only ever grows, and when it does (a larger
+  // chunk than any before) everything in flight is drained first, because the slots move.
+  const size_t in_need = ((size_t)chunk * clip_in * esz + 255) / 256 * 256;
+  const size_t out_need = mode == 0 ? ((size_t)chunk * clip_out * sizeof(float) + 255) / 256 * 256 : 0;
+  if (in_need > h->pipe_in_stride || out_need > h->pipe_out_stride || mode != h->pipe_last_mode) {
+    CK(cudaDeviceSynchronize());
+    h->pipe_last_mode = mode;
+    h->pipe_in_stride = std::max(h->pipe_in_stride, in_need);
+    h->pipe_out_stride = std::max(h->pipe_out_stride, out_need);
+  }
+  const size_t in_stride = h->pipe_in_stride;
+  const size_t out_stride = h->pipe_out_stride;
   const size_t pad_bytes = frame_paddings ? ((size_t)B * T * sizeof(float) + 255) / 256 * 256 : 0;
   CK(h->ws_io_in.ensure(2 * in_stride + 256 + pad_bytes));
   CK(h->ws_io_out.ensure(mode == 0 ? 2 * out_stride * (spatial_features ? 2 : 1) : (size_t)B * D * sizeof(float)));
