@@ -1653,6 +1653,11 @@ size_t vp_workspace_bytes(const vp_handle* h, int B, int T, int H, int W) {
   }
   const size_t M = clips * tokens_per_clip;
   const size_t D = c.model_dim, F = c.mlp_dim;
+  if (h->check_fp32) {   // fp32 check mode: x, n, qkv (3D), u and the patch matrix in float32 (+ the pooling head's scratch)
+    size_t bytes32 = M * (5 * D + F + h->k_patch) * sizeof(float);
+    if (c.kind != VP_KIND_ENCODER) bytes32 += (clips * tokens_per_clip * c.num_heads + clips * (size_t)c.num_heads * D + clips * ((size_t)c.num_heads * h->pool_ph + 2 * D)) * sizeof(float);
+    return bytes32;
+  }
   size_t bytes = M * (5 * D + F + h->k_patch_pad) * sizeof(bf16);                 // x, n, qkv (3D), u, patches
   const size_t slots = std::max(vp::gemm_stats_slots((int)D), 16);
   bytes += 2 * (M * 2 * slots + 64) * sizeof(float);                              // LayerNorm row statistics (two buffers)
