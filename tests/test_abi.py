@@ -45,3 +45,21 @@ def test_no_cpu_fallback(built_lib):
     assert "CUDA" in str(ei.value) or "device" in str(ei.value)
     import videoprism_b200._lib as L
     assert L.lib().vp_device_sm_count() < 0
+
+
+def test_header_is_valid_c_and_a_c_caller_links_and_runs(built_lib, tmp_path):
+    """examples/abi_smoke.c: the header compiles as C99 and a plain C program links against the library and gets the
+    documented behaviour (no CUDA device here: vp_create_ex fails loudly with VP_ERR_CUDA)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(built_lib)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_smoke.c"),
+                        "-L" + libdir, "-lvideoprism_b200", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "failed loudly" in r.stdout or "parameter leaves" in r.stdout
