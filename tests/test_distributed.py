@@ -59,9 +59,9 @@ def _worker(rank, world, port, n_video, n_text, dim, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_video,n_text", [(8, 16), (7, 5)])   # even and ragged shards
-def test_all_gather_of_sharded_embeddings_world2(tmp_path, n_video, n_text):
-    world, dim = 2, 24
+@pytest.mark.parametrize("world,n_video,n_text", [(2, 8, 16), (2, 7, 5), (3, 7, 5)])   # even and ragged shards; 3 ranks
+def test_all_gather_of_sharded_embeddings_world2(tmp_path, world, n_video, n_text):
+    dim = 24
     mp.spawn(_worker, args=(world, _free_port(), n_video, n_text, dim, str(tmp_path)), nprocs=world, join=True)
     assert all(open(tmp_path / f"ok_{r}").read() == "1" for r in range(world))
     sims = [np.load(tmp_path / f"sim_{r}.npy") for r in range(world)]
