@@ -66,8 +66,10 @@ def test_async_video_text_embeddings_match_the_blocking_call():
     m.load_state(W)
     a = O.make_video(5, 4, 16, seed=51, kind="normal")
     b = O.make_video(2, 4, 16, seed=52, kind="normal")
-    want_a, _, _ = m(a)
-    want_b, _, _ = m(b)
+    t, want_a = m.embed_video_async(a); m.wait(t)          # one at a time (same chunk schedule as below: 5 clips in one chunk)
+    t, want_b = m.embed_video_async(b); m.wait(t)
+    blocking, _, _ = m(a)                                   # the blocking call chunks 2 / 1 / 2: same numbers up to bf16-level noise
+    assert np.abs(blocking - want_a).max() < 2e-3
     ta, got_a = m.embed_video_async(a)
     tb, got_b = m.embed_video_async(b)                     # second call enqueued while the first is in flight
     m.wait(tb); m.wait(ta)
@@ -76,5 +78,4 @@ def test_async_video_text_embeddings_match_the_blocking_call():
     dev, _, _ = m(torch.from_numpy(a).cuda(), frame_paddings=torch.from_numpy(fp).cuda())
     t, host = m.embed_video_async(a, frame_paddings=fp)    # host path with frame paddings (new this round)
     m.wait(t)
-    # the device call runs the 5 clips in one pass, the host call in chunks of 2 / 1 / 2: same numbers up to bf16-level noise
     assert np.abs(host - dev.cpu().numpy()).max() < 2e-3

@@ -1252,13 +1252,18 @@ static int pipe_setup(vp_handle* h) {
   return VP_OK;
 }
 
-// Chunk schedule.  Within one call only the first chunk's H2D and the last chunk's D2H are exposed (everything else
-// overlaps the forward of a neighbouring chunk), so both ends are small (2 clips); every chunk costs ~0.4 ms of fixed
-// per-launch overhead (84 launches), so the middle runs 8-clip chunks with 6-clip ramps: 32 clips -> 2 6 8 8 6 2.
-static std::vector<int> chunk_schedule(const vp_handle* h, int B) {
+// Chunk schedule.  BLOCKING call (`ramp`): only the first chunk's H2D and the last chunk's D2H are exposed (everything
+// else overlaps the forward of a neighbouring chunk), so both ends are small (2 clips); every chunk costs fixed launch
+// overhead and small chunks run the GEMMs less efficiently, so the middle runs 8-clip chunks with 6-clip ramps:
+// 32 clips -> 2 6 8 8 6 2.  ASYNCHRONOUS call: the ends overlap the neighbouring CALLS' forwards, so there is nothing to
+// ramp: equal chunks of at most 8 clips (32 -> 8 8 8 8, 8 -> 8, 12 -> 6 6).
+static std::vector<int> chunk_schedule(const vp_handle* h, int B, bool ramp) {
   std::vector<int> sizes;
   if (h->host_chunk_clips > 0) {
     for (int c0 = 0; c0 < B; c0 += h->host_chunk_clips) sizes.push_back(B - c0 < h->host_chunk_clips ? B - c0 : h->host_chunk_clips);
+  } else if (!ramp && B > 4) {
+    const int n = (B + 7) / 8;
+    for (int i = 0; i < n; ++i) sizes.push_back(B / n + (i < B % n ? 1 : 0));
   } else if (B <= 4) {
     for (int c0 = 0; c0 < B; c0 += 2) sizes.push_back(B - c0 < 2 ? B - c0 : 2);
   } else {
@@ -1285,7 +1290,8 @@ static int clip_video_forward_dev(vp_handle* h, const void* video, int in_dtype,
 // mode 0: encoder features (out_dtype VP_F32 / VP_BF16, optional fp32 spatial_features); mode 1: video-text model, pooled
 // video embeddings [B, D] fp32 (`normalize`).  Enqueues everything and records the call's completion event; no host wait.
 static int host_pipeline(vp_handle* h, int mode, const void* video_v, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
-                         void* out_v, float* spatial_features, int out_dtype, int normalize, cudaStream_t st, uint64_t* ticket) {
+                         void* out_v, float* spatial_features, int out_dtype, int normalize, cudaStream_t st, uint64_t* ticket,
+                         bool ramp) {
   const char* video = static_cast<const char*>(video_v);
   const size_t esz = in_dtype == VP_U8 ? 1 : sizeof(float);
   int rc = check_ready(h);
@@ -1302,7 +1308,7 @@ static int host_pipeline(vp_handle* h, int mode, const void* video_v, int in_dty
   const size_t D = h->cfg.model_dim;
   const size_t clip_out = (size_t)T * N * D;
   const size_t osz = out_dtype == VP_BF16 ? sizeof(bf16) : sizeof(float);
-  const std::vector<int> sizes = chunk_schedule(h, B);
+  const std::vector<int> sizes = chunk_schedule(h, B, ramp);
   const int nchunks = (int)sizes.size();
   int chunk = 0;
   for (int c : sizes) chunk = c > chunk ? c : chunk;
@@ -1392,7 +1398,7 @@ int vp_encoder_forward_host_async(vp_handle* h, const void* video, int in_dtype,
   DeviceScope device_scope(h ? h->device : -1);
   if (h == nullptr) return VP_ERR_INVALID;
   return host_pipeline(h, 0, video, in_dtype, B, T, H, W, frame_paddings, out_features, spatial_features, out_dtype, 0,
-                       static_cast<cudaStream_t>(stream), ticket);
+                       static_cast<cudaStream_t>(stream), ticket, /*ramp=*/false);
 }
 
 int vp_clip_video_forward_host_async(vp_handle* h, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
@@ -1400,7 +1406,7 @@ int vp_clip_video_forward_host_async(vp_handle* h, const void* video, int in_dty
   DeviceScope device_scope(h ? h->device : -1);
   if (h == nullptr) return VP_ERR_INVALID;
   return host_pipeline(h, 1, video, in_dtype, B, T, H, W, frame_paddings, video_emb, nullptr, VP_F32, normalize,
-                       static_cast<cudaStream_t>(stream), ticket);
+                       static_cast<cudaStream_t>(stream), ticket, /*ramp=*/false);
 }
 
 static int host_sync_call(vp_handle* h, int mode, const void* video, int in_dtype, int B, int T, int H, int W, const float* frame_paddings,
@@ -1409,7 +1415,7 @@ static int host_sync_call(vp_handle* h, int mode, const void* video, int in_dtyp
   if (h == nullptr) return VP_ERR_INVALID;
   uint64_t tk = 0;
   int rc = host_pipeline(h, mode, video, in_dtype, B, T, H, W, frame_paddings, out, spatial_features, VP_F32, normalize,
-                         static_cast<cudaStream_t>(stream), &tk);
+                         static_cast<cudaStream_t>(stream), &tk, /*ramp=*/true);
   if (rc != VP_OK) return rc;
   CK(cudaEventSynchronize(h->ev_done[tk % vp_handle::kTickets]));
   CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));

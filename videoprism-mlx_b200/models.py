@@ -321,8 +321,21 @@ class FactorizedEncoder(_Module):
                                                   _lib.VP_BF16 if bf16_out else _lib.VP_F32, self._stream_ptr()), h)
             outs = {"spatial_features": sp} if want_spatial else {}
             return out, outs
-        ticket, out, outs = self.forward_async(inputs, return_intermediate=return_intermediate, frame_paddings=frame_paddings, out=out)
-        self.wait(ticket)
+        # blocking host call (vp_encoder_forward_host): its chunk schedule ramps at both ends, because nothing outside this call
+        # overlaps its first copy in and its last copy out; forward_async below is the form whose calls overlap each other
+        is_u8 = np.asarray(inputs).dtype == np.uint8
+        x = np.ascontiguousarray(np.asarray(inputs), dtype=np.uint8 if is_u8 else np.float32)
+        fwd_host = lib.vp_encoder_forward_host_u8 if is_u8 else lib.vp_encoder_forward_host
+        if out is None:
+            out = np.empty((b, t * n, d), dtype=np.float32)
+        elif out.shape != (b, t * n, d) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a C-contiguous float32 array of shape {(b, t * n, d)}")
+        sp = np.empty_like(out) if want_spatial else None
+        fp = None if frame_paddings is None else np.ascontiguousarray(np.asarray(frame_paddings), dtype=np.float32)
+        _lib.check(fwd_host(
+            h, x.ctypes.data_as(C.c_void_p), b, t, hh, ww, None if fp is None else fp.ctypes.data_as(C.c_void_p),
+            out.ctypes.data_as(C.c_void_p), None if sp is None else sp.ctypes.data_as(C.c_void_p), None), h)
+        outs = {"spatial_features": sp} if want_spatial else {}
         return out, outs
 
     def forward_async(self, inputs, return_intermediate: bool | Collection[str] = False, frame_paddings=None, out=None,
@@ -408,8 +421,14 @@ class FactorizedVideoCLIP(_Module):
                     video_emb = v.cpu().numpy()
                     outs.update({k: a.cpu().numpy() for k, a in o.items()})
                 else:
-                    ticket, video_emb = self.embed_video_async(inputs, frame_paddings=frame_paddings, normalize=normalize)
-                    self.wait(ticket)
+                    if frame_paddings is None and np.asarray(inputs).dtype != np.uint8:
+                        x = np.ascontiguousarray(np.asarray(inputs), dtype=np.float32)      # blocking call, ramped chunk schedule
+                        video_emb = np.empty((b, d), dtype=np.float32)
+                        _lib.check(lib.vp_clip_video_forward_host(h, x.ctypes.data_as(C.c_void_p), b, t, hh, ww, int(bool(normalize)),
+                                                                  video_emb.ctypes.data_as(C.c_void_p), None), h)
+                    else:                                                                    # uint8 frames / frame paddings
+                        ticket, video_emb = self.embed_video_async(inputs, frame_paddings=frame_paddings, normalize=normalize)
+                        self.wait(ticket)
         if text_token_ids is not None:
             assert text_paddings is not None, "Text paddings are required."  # encoders.py:888
             if text_token_ids.ndim != 2 or tuple(text_paddings.shape) != tuple(text_token_ids.shape):
