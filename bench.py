@@ -18,6 +18,7 @@ timed region), `roofline` is the dominant kernel (FFN1 GEMM) against the measure
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -303,7 +304,7 @@ def run_retrieval(args):
     numa_node = bind_to_gpu_numa_node(local)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))   # a mismatched collective aborts in minutes, not in NCCL's default 10
     import videoprism_b200 as vp
     from videoprism_b200.retrieval import gather_embedding_pair, retrieval_similarity, shard_range
     name = {"base": "videoprism_lvt_public_v1_base", "large": "videoprism_lvt_public_v1_large"}[args.model]
@@ -484,7 +485,7 @@ def main():
     numa_node = bind_to_gpu_numa_node(local)   # before any pinned allocation
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout: stdout carries ONE JSON line
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))   # a mismatched collective aborts in minutes, not in NCCL's default 10
     warmup = max(args.warmup, 3)
 
     import videoprism_b200 as vp
