@@ -1,3 +1,6 @@
+# NOTE: this is the call that spent the rest of the round's GPU budget: the retrieval bench of that commit ran two extra steps WITH the
+# all-gather on rank 0 alone (trace leg), NCCL waited 10 minutes per run, and 8 GPUs are charged 8x.  Fixed in bench.py (the trace
+# leg runs the forward without the collective; 4-minute NCCL timeout); the first three bench lines below are valid measurements.
 export MASTER_ADDR=127.0.0.1
 timeout 600 python -m pytest tests/test_retrieval_nccl_gpu.py tests/test_parity_gpu.py -m gpu -x -q -k "nccl or two_devices" -s 2>&1 | tail -12 > gpurun_out/r2j_pytest_multi.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2j_bench_base_8gpu.json 2> gpurun_out/r2j_bench_base_8gpu.err
